@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- land-cell-timesteps/s of the HYDROLOGY+GROW path (BASELINE.json metric).
+
+One "step" = one simulated year (365 days x NISURF=48 sub-steps) over every land
+cell of the rank's block: forcing derivation, 48 x HYDROLOGY, GROW, annual
+accumulators -- the loop nest HYBRID9.f90:120-295.  Workload at N=1: the 0.5 deg
+global land mask (67,420 cells), configs[2] of BASELINE.json, on synthetic
+PGF-shaped forcing (hybrid9_b200/synth.py).
+
+  value  device-resident: compact forcing already in HBM, one fused launch per
+         year (h9_run_days_device); CUDA events on the launching stream.
+  e2e    through h9_run_days with the seven (lon_c,lat_c,ndays) HOST arrays as
+         READ_PGF leaves them (pinned), host->device copies and the device-side
+         pack inside the timed region, plus the device->host read of the year's
+         annual means (h9_get_annual) and the fault word.
+  roofline  352 algorithmic bytes per land-cell-timestep over the
+         fused kernel's CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle's -O3 build (C++ restatement standing in for
+         `mpif90 -O3`, which cannot be built here) on all host cores, bounded sample.
+
+`--impl reference` times that CPU restatement alone (rank 0), same metric/config.
+Multi-GPU: one process per GPU (torchrun), each rank a full 0.5 deg block
+(weak scaling; `--scaling strong` shards one block in latitude bands instead);
+the only collectives are the per-year annual-mean all-gather and the FP64
+budget all-reduce, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_CELL_STEP = 352.0
+METRIC = "land_cell_timesteps_per_s"
+UNIT = "cell-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--grid", default="0.5", choices=["0.5", "0.25", "regional", "tiny"])
+    ap.add_argument("--days", type=int, default=365)
+    ap.add_argument("--nisurf", type=int, default=48)
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--tile-days", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def grid_spec(name):
+    if name == "0.5":
+        return dict(nx=720, ny=360, n_land=67420, label="0.5deg global land mask")
+    if name == "0.25":
+        return dict(nx=1440, ny=720, n_land=269680, label="0.25deg global land mask")
+    if name == "regional":
+        return dict(nx=720, ny=360, n_land=67420, label="regional 100x74 window of the 0.5deg mask",
+                    window=(340, 37, 100, 74))
+    return dict(nx=72, ny=36, n_land=674, label="tiny 5deg test grid")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(world, forcing, nisurf, seconds, kind_note=""):
+    """Time the oracle's -O3 build on all host cores over a bounded sample of the
+    same workload (first cells of the block, first days of the year)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+    from hybrid9_b200 import synth
+    cores = os.cpu_count() or 1
+    ncell = int(min(world.land.sum(), 256 * cores))
+    days_avail = forcing["tas"].shape[0]
+
+    def run(nd):
+        cw = synth.compact_world(world, ncell)
+        cf = synth.compact_forcing(world, forcing, ncell, ndays=nd)
+        o = oracle_py.Oracle("o3")
+        o.configure(cw.nx, cw.ny, nisurf, synth.ZI_DRIVER, nyr=1)
+        o.set_soil(cw.soil_tex, cw.theta_s, cw.hksat, cw.bsw, cw.psi_s, cw.fmax)
+        o.init_state()
+        o.set_options(loop_order=0, smp_leak=0, nthreads=cores)  # the reference's cell-outer order
+        t = time.perf_counter()
+        o.run_days(np.ones(nd, np.int32), cf)
+        dt = time.perf_counter() - t
+        o.close()
+        return ncell * nd * nisurf / dt, dt
+
+    rate, _ = run(min(2, days_avail))
+    nd = int(max(2, min(days_avail, seconds * rate / (ncell * nisurf))))
+    rate, dt = run(nd)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ncell} land cells x {nd} days x {nisurf} sub-steps, cell-outer loop order, "
+                      f"{cores} threads, g++ -O3 -march=x86-64-v3 C++ restatement of "
+                      f"HYDROLOGY.f90/GROW.f90 (no Fortran compiler in the image){kind_note}",
+            "seconds": dt}
+
+
+def build_world(args):
+    from hybrid9_b200 import synth
+    g = grid_spec(args.grid)
+    w = synth.make_world(nx=g["nx"], ny=g["ny"], n_land=g["n_land"], seed=9)
+    if "window" in g:
+        w = w.window(*g["window"])
+    return w, g["label"]
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement alone, rank 0 only."""
+    if rank != 0:
+        return
+    from hybrid9_b200 import synth
+    world, label = build_world(args)
+    cores = os.cpu_count() or 1
+    ncell = int(min(world.land.sum(), 256 * cores))
+    sample_days = min(args.days, 120)
+    cw = synth.compact_world(world, ncell)
+    forcing = synth.make_forcing(cw, sample_days, seed=9)
+    # size one step to a few seconds of CPU work (whole run within ~2 minutes)
+    probe = cpu_baseline(cw, forcing, args.nisurf, 1.0)
+    per_step = max(1.0, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
+    nd = int(max(2, min(sample_days, per_step * probe["value"] / (ncell * args.nisurf))))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+    cf = {k: np.ascontiguousarray(v[:nd]) for k, v in forcing.items()}
+    o = oracle_py.Oracle("o3")
+    o.configure(cw.nx, cw.ny, args.nisurf, synth.ZI_DRIVER, nyr=1)
+    o.set_soil(cw.soil_tex, cw.theta_s, cw.hksat, cw.bsw, cw.psi_s, cw.fmax)
+    o.init_state()
+    o.set_options(loop_order=0, smp_leak=0, nthreads=cores)
+    yi = np.ones(nd, np.int32)
+    for _ in range(args.warmup):
+        o.run_days(yi, cf)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.run_days(yi, cf)
+    dt = time.perf_counter() - t
+    units = ncell * nd * args.nisurf * args.steps
+    value = units / dt
+    sample = (f"{ncell} land cells x {nd} days x {args.nisurf} sub-steps per step, cell-outer "
+              f"loop order, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{label}, {args.days} d x {args.nisurf} sub-steps "
+                               f"(bounded CPU sample: {sample})"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; g++ -O3 C++ restatement of HYDROLOGY.f90/GROW.f90 "
+                                            "(the Fortran reference cannot be compiled in this image)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hybrid9_b200 import H9, MATH_EXACT, MATH_FAST, synth
+    from hybrid9_b200.host import pinned_empty
+    from hybrid9_b200.state import init_state
+    from hybrid9_b200 import distributed as h9d
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the HYDROLOGY/GROW path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    multi = world_size > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+
+    world, label = build_world(args)
+    lat_s = 1
+    if multi and args.scaling == "strong":
+        world, lat_s, _, n_land_all = h9d.shard_world(world, rank, world_size)
+    nd, nis = args.days, args.nisurf
+    nc = int(world.land.sum())
+    n_land_all = [nc] * world_size
+    if multi:
+        t = torch.tensor([nc], device=dev, dtype=torch.int64)
+        parts = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(parts, t)
+        n_land_all = [int(p.item()) for p in parts]
+
+    # host forcing exactly as READ_PGF leaves it, in pinned memory
+    names = ("tas", "rlds", "rsds", "huss", "ps", "pr", "rhs")
+    forcing = {k: pinned_empty((nd, world.ny, world.nx)) for k in names}
+    synth.make_forcing(world, nd, seed=9 + rank, out=forcing)
+
+    h = H9(local_rank)
+    nyr = 2
+    h.configure(world.nx, world.ny, nis, synth.ZI_DRIVER, nyr=nyr)
+    h.set_math(MATH_EXACT if args.math == "exact" else MATH_FAST)
+    h.set_tuning(args.tile_days, args.block)
+    h.set_soil(world.soil_tex, world.theta_s, world.hksat, world.bsw, world.psi_s, world.fmax)
+    assert h.num_land == nc
+    h.set_state(init_state(world.soil_tex, world.theta_s, synth.ZI_DRIVER), with_smp=False)
+    d_forc, day_stride, plane_stride = h.pack_forcing(forcing, nd)
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    year = [0]
+
+    def collective(iy):
+        if multi:
+            h9d.h9_annual_collective(h, iy, n_land_all, device=dev)
+
+    def step_device():
+        year[0] += 1
+        iy = (year[0] - 1) % nyr + 1
+        rc = h.run_days_device(np.full(nd, iy, np.int32), d_forc, day_stride, plane_stride)
+        if rc:
+            raise SystemExit(f"physics fault {rc}: {h.get_fault()}")
+        collective(iy)
+
+    def step_e2e():
+        year[0] += 1
+        iy = (year[0] - 1) % nyr + 1
+        rc = h.run_days(np.full(nd, iy, np.int32), forcing)
+        if rc:
+            raise SystemExit(f"physics fault {rc}: {h.get_fault()}")
+        ann = h.get_annual(iy)
+        collective(iy)
+        return ann
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        h.synchronize()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        h.reset_counters()
+        cs = ClockSampler(local_rank) if sample_clocks else None
+        if cs:
+            cs.start()
+            time.sleep(0.25)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        h.synchronize()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if multi:
+            dist.barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        clocks = cs.stop() if cs else None
+        cnt = h.counters()
+        if multi:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, cnt, clocks
+
+    units_rank = nc * nd * nis
+    units_all = sum(n_land_all) * nd * nis
+
+    ms, wall, cnt, clocks = timed(step_device, args.steps, max(args.warmup, 3), sample_clocks=True)
+    ms_per_step = ms / args.steps
+    value = units_all / (ms_per_step * 1e-3)
+    kern_ms = cnt["step_kernel_ms"] / max(1, args.steps)  # fused kernel, CUDA events, this rank
+    peak, peak_src = peaks()
+    achieved = units_rank * BYTES_PER_CELL_STEP / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel": "h9::days_kernel",
+                "kernel_ms_per_launch": kern_ms, "launches_per_step": cnt["launches"] / args.steps,
+                "algorithmic_bytes_per_unit": BYTES_PER_CELL_STEP, "peak_source": peak_src,
+                "note": "algorithmic roofline of a per-sub-step operator; the fused kernel keeps "
+                        "state in registers, real DRAM traffic is the forcing stream (see "
+                        "profiles/), the binding limiters are the FP32/MUFU pipes"}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                tj = json.load(f)
+            # measured dram bytes per land-cell-timestep from the committed ncu capture
+            roofline["traffic"] = float(tj["dram_bytes_per_cell_step"]) * units_rank
+            roofline["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+    launches = cnt["launches"]
+
+    e2e = None
+    if not args.no_e2e:
+        ems, ewall, ecnt, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        e_ms = max(ems, ewall * 1e3) / args.steps
+        e2e = {"value": units_all / (e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": ecnt["h2d_bytes"] // args.steps,
+               "d2h_bytes_per_step": ecnt["d2h_bytes"] // args.steps,
+               "ms_per_step": e_ms, "gpu_launches": ecnt["launches"],
+               "api": "h9_run_days (pinned host forcing as READ_PGF leaves it) + h9_get_annual"}
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline(world, forcing, nis, args.cpu_seconds)
+        except Exception as ex:  # the checker is test infrastructure; never fail the bench on it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{label}: {nc} land cells x {nd} days x {nis} sub-steps per "
+                                   f"step per GPU" if args.scaling == "weak" else
+                                   f"{label} sharded in latitude bands: {sum(n_land_all)} land cells "
+                                   f"x {nd} days x {nis} sub-steps per step",
+                       "land_cells_per_gpu": n_land_all, "days_per_step": nd, "nisurf": nis,
+                       "math": args.math,
+                       "l2": "forcing stream (689 MB/step at 0.5deg) exceeds L2; state is "
+                             "register/L2 resident by design",
+                       "parallelism": f"dp{world_size} latitude bands, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "wall_s_timed": wall,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,899 @@
+/*
+ * h9_api.cu -- the C-ABI of libh9gpu (include/h9gpu.h): context, land
+ * compaction, state upload/download, the forcing ingest pipeline and the
+ * launches of the time-stepping kernels.  No CPU implementation of the physics
+ * exists in this library: every compute entry launches CUDA kernels and fails
+ * with H9_ERR_CUDA when no device is usable.
+ *
+ * Replaces the loop nest HYBRID9.f90:120-295 of the reference's driver; see
+ * include/h9gpu.h for the per-entry citations.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/h9gpu.h"
+#include "h9_device.h"
+
+using namespace h9;
+
+namespace h9 {
+int launch_budget(void* stream, const DevArrays& a, int iyr, double* d_budget);
+}
+
+struct h9_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::string err;
+  bool configured = false, have_soil = false;
+  int lon_c = 0, lat_c = 0, nisurf = 48, nyr = 1;
+  size_t ngrid = 0;
+  int math_mode = H9_MATH_FAST;
+  int tile_days = 8, block = 64;
+  Geo geo;
+  std::vector<int32_t> cell_xy;
+  DevArrays dev;
+  int32_t* d_cell_xy = nullptr;
+  std::vector<void*> allocs; /* everything sized by the soil/land set */
+  /* year bookkeeping (all cells step in lockstep, so these are scalars) */
+  int cur_year = 0, nt = 0, max_year_seen = 0;
+  unsigned long long step_counter = 0;
+  /* forcing pipeline */
+  float* d_stage[2] = {nullptr, nullptr};
+  float* d_packed[2] = {nullptr, nullptr};
+  float* h_stage[2] = {nullptr, nullptr};
+  size_t stage_days = 0;
+  cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+              ev_h2d[2] = {nullptr, nullptr};
+  int32_t* d_year_index = nullptr;
+  size_t year_index_cap = 0;
+  float* d_pack_full = nullptr;
+  size_t pack_full_cap = 0;
+  float* d_step_forcing = nullptr; /* [7][ncs] for the fine-grained entries */
+  float* d_diag = nullptr;         /* [12][ncs] + jwt */
+  double* d_budget = nullptr;
+  /* counters */
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+  std::vector<cudaEvent_t> event_pool;
+  double step_ms = 0.0;
+};
+
+namespace {
+
+int fail(h9_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      return fail(ctx, H9_ERR_CUDA,                                                   \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ \
+                                                                         ")");        \
+    }                                                                                 \
+  } while (0)
+
+#define CKL(expr)                                                                         \
+  do {                                                                                    \
+    int e_ = (expr);                                                                      \
+    if (e_ != 0)                                                                          \
+      return fail(ctx, H9_ERR_CUDA,                                                       \
+                  std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)e_));      \
+    ctx->launches += 1;                                                                   \
+  } while (0)
+
+template <class T>
+int dev_alloc(h9_ctx* ctx, T** p, size_t n, bool track = true) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(ctx, H9_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(ctx, H9_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  *p = (T*)q;
+  if (track) ctx->allocs.push_back(q);
+  return 0;
+}
+
+void free_land(h9_ctx* ctx) {
+  for (void* q : ctx->allocs) cudaFree(q);
+  ctx->allocs.clear();
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->d_stage[b]) cudaFree(ctx->d_stage[b]);
+    if (ctx->d_packed[b]) cudaFree(ctx->d_packed[b]);
+    if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+    ctx->d_stage[b] = ctx->d_packed[b] = ctx->h_stage[b] = nullptr;
+  }
+  ctx->stage_days = 0;
+  if (ctx->d_pack_full) cudaFree(ctx->d_pack_full);
+  ctx->d_pack_full = nullptr;
+  ctx->pack_full_cap = 0;
+  ctx->d_cell_xy = nullptr;
+  ctx->d_step_forcing = nullptr;
+  ctx->d_diag = nullptr;
+  ctx->d_budget = nullptr;
+  memset(&ctx->dev, 0, sizeof(ctx->dev));
+  ctx->have_soil = false;
+}
+
+int set_device(h9_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  return 0;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+cudaEvent_t get_event(h9_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int launch_days(h9_ctx* ctx, int ndays, const int32_t* d_yi, const float* d_forcing,
+                size_t day_stride, size_t plane_stride) {
+  cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+  CK(cudaEventRecord(e0, ctx->stream));
+  if (ctx->math_mode == H9_MATH_EXACT) {
+    CKL(launch_days_exact(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, d_forcing, day_stride,
+                          plane_stride, ctx->cur_year, ctx->nt, ctx->step_counter, ctx->block));
+  } else {
+    CKL(launch_days_fast(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, d_forcing, day_stride,
+                         plane_stride, ctx->cur_year, ctx->nt, ctx->step_counter, ctx->block));
+  }
+  CK(cudaEventRecord(e1, ctx->stream));
+  ctx->timing.emplace_back(e0, e1);
+  return 0;
+}
+
+/* host mirror of the kernel's year bookkeeping */
+void advance_years(h9_ctx* ctx, int ndays, const int32_t* yi) {
+  for (int d = 0; d < ndays; ++d) {
+    if (yi[d] != ctx->cur_year) {
+      ctx->cur_year = yi[d];
+      ctx->nt = 0;
+    }
+    ctx->nt += 1;
+    ctx->max_year_seen = std::max(ctx->max_year_seen, (int)yi[d]);
+  }
+  ctx->step_counter += (unsigned long long)ndays * ctx->nisurf;
+}
+
+int upload_year_index(h9_ctx* ctx, int ndays, const int32_t* yi) {
+  if ((size_t)ndays > ctx->year_index_cap) {
+    if (ctx->d_year_index) cudaFree(ctx->d_year_index);
+    ctx->d_year_index = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_year_index, (size_t)ndays * sizeof(int32_t)));
+    ctx->year_index_cap = (size_t)ndays;
+  }
+  CK(cudaMemcpyAsync(ctx->d_year_index, yi, (size_t)ndays * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d += (int64_t)ndays * 4;
+  return 0;
+}
+
+int read_any_fault(h9_ctx* ctx, uint32_t* any) {
+  CK(cudaMemcpyAsync(any, ctx->dev.any_fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h += 4;
+  return 0;
+}
+
+int ensure_stage(h9_ctx* ctx, bool need_host_stage) {
+  const size_t td = (size_t)ctx->tile_days;
+  if (ctx->stage_days != td) {
+    for (int b = 0; b < 2; ++b) {
+      if (ctx->d_stage[b]) cudaFree(ctx->d_stage[b]);
+      if (ctx->d_packed[b]) cudaFree(ctx->d_packed[b]);
+      if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+      ctx->d_stage[b] = ctx->d_packed[b] = ctx->h_stage[b] = nullptr;
+      CK(cudaMalloc((void**)&ctx->d_stage[b], td * kForcingPlanes * ctx->ngrid * sizeof(float)));
+      CK(cudaMalloc((void**)&ctx->d_packed[b], td * kForcingPlanes * ctx->dev.ncs * sizeof(float)));
+    }
+    ctx->stage_days = td;
+  }
+  if (need_host_stage && !ctx->h_stage[0]) {
+    for (int b = 0; b < 2; ++b)
+      CK(cudaMallocHost((void**)&ctx->h_stage[b], td * kForcingPlanes * ctx->ngrid * sizeof(float)));
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (!ctx->ev_packed[b]) CK(cudaEventCreateWithFlags(&ctx->ev_packed[b], cudaEventDisableTiming));
+    if (!ctx->ev_done[b]) CK(cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
+    if (!ctx->ev_h2d[b]) CK(cudaEventCreateWithFlags(&ctx->ev_h2d[b], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+/* copy days [d0,d0+nd) of the seven (lon_c,lat_c,ndays) host arrays into stage
+ * buffer b as [7][nd][ngrid] and pack them into `d_out` ([nd][7][ncs]) on the
+ * copy stream */
+int stage_and_pack(h9_ctx* ctx, int b, int d0, int nd, const float* const src[7], bool pinned,
+                   float* d_out) {
+  const size_t plane = (size_t)nd * ctx->ngrid;
+  for (int p = 0; p < kForcingPlanes; ++p) {
+    const float* hp = src[p] + (size_t)d0 * ctx->ngrid;
+    if (!pinned) { /* pageable caller memory: bounce through our pinned ring */
+      memcpy(ctx->h_stage[b] + p * plane, hp, plane * sizeof(float));
+      hp = ctx->h_stage[b] + p * plane;
+    }
+    CK(cudaMemcpyAsync(ctx->d_stage[b] + p * plane, hp, plane * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->h2d += (int64_t)(plane * sizeof(float));
+  }
+  CK(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
+  CKL(launch_pack_forcing(ctx->copy_stream, ctx->d_stage[b], nd, ctx->ngrid, ctx->d_cell_xy,
+                          ctx->dev.nc, ctx->dev.ncs, d_out));
+  return 0;
+}
+
+template <class T>
+void gather(const h9_ctx* ctx, const T* src, int per, int take, std::vector<T>& out) {
+  /* Fortran (per,lon_c,lat_c) -> compact [ncs][take] */
+  out.assign((size_t)ctx->dev.ncs * take, T(0));
+  for (int k = 0; k < ctx->dev.nc; ++k) {
+    const size_t ci = (size_t)ctx->cell_xy[k];
+    for (int i = 0; i < take; ++i) out[(size_t)k * take + i] = src[ci * per + i];
+  }
+}
+
+template <class T>
+void scatter(const h9_ctx* ctx, const T* compact, int take, int per, T* dst) {
+  for (int k = 0; k < ctx->dev.nc; ++k) {
+    const size_t ci = (size_t)ctx->cell_xy[k];
+    for (int i = 0; i < take; ++i) dst[ci * per + i] = compact[(size_t)k * take + i];
+  }
+}
+
+template <class T>
+int upload(h9_ctx* ctx, T* d, const std::vector<T>& h) {
+  CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->h2d += (int64_t)(h.size() * sizeof(T));
+  return 0;
+}
+
+template <class T>
+int download(h9_ctx* ctx, std::vector<T>& h, const T* d, size_t n) {
+  h.resize(n);
+  CK(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h += (int64_t)(n * sizeof(T));
+  return 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int h9_create(h9_ctx** out, int device_id) {
+  if (!out) return H9_ERR_ARG;
+  *out = nullptr;
+  h9_ctx* ctx = new h9_ctx();
+  memset(&ctx->dev, 0, sizeof(ctx->dev));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    /* no CPU path exists: creation fails loudly */
+    fprintf(stderr, "libh9gpu: no usable CUDA device (%s)\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    delete ctx;
+    return H9_ERR_CUDA;
+  }
+  if (device_id < 0) {
+    if (cudaGetDevice(&ctx->device) != cudaSuccess) ctx->device = 0;
+  } else {
+    ctx->device = device_id;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fprintf(stderr, "libh9gpu: cannot initialise device %d: %s\n", ctx->device,
+            cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return H9_ERR_CUDA;
+  }
+  const char* td = getenv("H9_TILE_DAYS");
+  if (td && atoi(td) > 0) ctx->tile_days = atoi(td);
+  const char* bl = getenv("H9_BLOCK");
+  if (bl && (atoi(bl) == 32 || atoi(bl) == 64 || atoi(bl) == 128)) ctx->block = atoi(bl);
+  *out = ctx;
+  return H9_OK;
+}
+
+int h9_destroy(h9_ctx* ctx) {
+  if (!ctx) return H9_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_land(ctx);
+  if (ctx->d_year_index) cudaFree(ctx->d_year_index);
+  for (auto& pr : ctx->timing) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_packed[b]) cudaEventDestroy(ctx->ev_packed[b]);
+    if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
+    if (ctx->ev_h2d[b]) cudaEventDestroy(ctx->ev_h2d[b]);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return H9_OK;
+}
+
+const char* h9_last_error(const h9_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int h9_configure(h9_ctx* ctx, int lon_c, int lat_c, int nisurf, const float zi[10], int nyr) {
+  if (!ctx) return H9_ERR_ARG;
+  if (lon_c < 1 || lat_c < 1 || nisurf < 1 || !zi || nyr < 1)
+    return fail(ctx, H9_ERR_ARG, "h9_configure: bad argument");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  free_land(ctx);
+  ctx->lon_c = lon_c;
+  ctx->lat_c = lat_c;
+  ctx->nisurf = nisurf;
+  ctx->nyr = nyr;
+  ctx->ngrid = (size_t)lon_c * lat_c;
+  geo_init(ctx->geo, zi, nisurf);
+  ctx->cur_year = 0;
+  ctx->nt = 0;
+  ctx->max_year_seen = 0;
+  ctx->step_counter = 0;
+  ctx->configured = true;
+  return H9_OK;
+}
+
+int h9_set_math(h9_ctx* ctx, int mode) {
+  if (!ctx) return H9_ERR_ARG;
+  if (mode != H9_MATH_EXACT && mode != H9_MATH_FAST) return fail(ctx, H9_ERR_ARG, "h9_set_math: bad mode");
+  ctx->math_mode = mode;
+  return H9_OK;
+}
+
+int h9_set_tuning(h9_ctx* ctx, int tile_days, int block) {
+  if (!ctx) return H9_ERR_ARG;
+  if (tile_days > 0) ctx->tile_days = tile_days;
+  if (block == 32 || block == 64 || block == 128) ctx->block = block;
+  return H9_OK;
+}
+
+int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, const float* hksat,
+                const float* bsw, const float* psi_s, const float* fmax) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->configured) return fail(ctx, H9_ERR_STATE, "h9_set_soil: call h9_configure first");
+  if (!soil_tex || !theta_s || !hksat || !bsw || !psi_s || !fmax)
+    return fail(ctx, H9_ERR_ARG, "h9_set_soil: null pointer");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  free_land(ctx);
+  /* land predicate and iteration order of HYBRID9.f90:120-123: y outer, x inner,
+   * SUM(theta_s(:,x,y)) in index order, in float */
+  ctx->cell_xy.clear();
+  for (int y = 0; y < ctx->lat_c; ++y)
+    for (int x = 0; x < ctx->lon_c; ++x) {
+      const size_t ci = (size_t)y * ctx->lon_c + x;
+      volatile float sum = 0.0f;
+      for (int i = 0; i < NL; ++i) sum = sum + theta_s[ci * NL + i];
+      if (soil_tex[ci] > 0 && soil_tex[ci] != 13 && sum > 1.0E-8f) ctx->cell_xy.push_back((int32_t)ci);
+    }
+  DevArrays& d = ctx->dev;
+  d.nc = (int)ctx->cell_xy.size();
+  d.ncs = std::max(kCellPad, (d.nc + kCellPad - 1) / kCellPad * kCellPad);
+  d.nyr = ctx->nyr;
+  const size_t n = (size_t)d.ncs;
+  int rc = 0;
+  float *ths = nullptr, *hks = nullptr, *bs = nullptr, *ps = nullptr, *fm = nullptr;
+  rc |= dev_alloc(ctx, &d.h2o, n * NL);
+  rc |= dev_alloc(ctx, &d.smp, n * NL);
+  rc |= dev_alloc(ctx, &d.rootr, n * NL);
+  rc |= dev_alloc(ctx, &ths, n * NL);
+  rc |= dev_alloc(ctx, &hks, n * NL);
+  rc |= dev_alloc(ctx, &bs, n * NL);
+  rc |= dev_alloc(ctx, &ps, n * NL);
+  rc |= dev_alloc(ctx, &fm, n);
+  rc |= dev_alloc(ctx, &d.zwt, n);
+  rc |= dev_alloc(ctx, &d.wa, n);
+  rc |= dev_alloc(ctx, &d.lai, n);
+  rc |= dev_alloc(ctx, &d.lai_litter, n);
+  rc |= dev_alloc(ctx, &d.plant_mass, n);
+  rc |= dev_alloc(ctx, &d.plant_foliage_mass, n);
+  rc |= dev_alloc(ctx, &d.plant_length, n);
+  rc |= dev_alloc(ctx, &d.rdepth, n);
+  rc |= dev_alloc(ctx, &d.nplants, n);
+  rc |= dev_alloc(ctx, &d.rnf_sum, n);
+  rc |= dev_alloc(ctx, &d.npp_sum, n);
+  rc |= dev_alloc(ctx, &d.plant_mass_sum, n);
+  rc |= dev_alloc(ctx, &d.h2osoi_sum_total, n);
+  rc |= dev_alloc(ctx, &d.theta_sum, n * NL);
+  rc |= dev_alloc(ctx, &d.annual, (size_t)d.nyr * kAnnualPlanes * n);
+  rc |= dev_alloc(ctx, &d.fault, n);
+  rc |= dev_alloc(ctx, &d.first_code, n);
+  rc |= dev_alloc(ctx, &d.first_step, n);
+  rc |= dev_alloc(ctx, &d.first_imb, n);
+  rc |= dev_alloc(ctx, &d.first_key, 1);
+  rc |= dev_alloc(ctx, &d.any_fault, 1);
+  rc |= dev_alloc(ctx, &ctx->d_cell_xy, n);
+  rc |= dev_alloc(ctx, &ctx->d_step_forcing, n * kForcingPlanes);
+  rc |= dev_alloc(ctx, &ctx->d_diag, n * 13);
+  rc |= dev_alloc(ctx, &ctx->d_budget, 8);
+  if (rc) {
+    free_land(ctx);
+    return rc < 0 ? (rc == H9_ERR_NOMEM ? H9_ERR_NOMEM : H9_ERR_CUDA) : H9_ERR_CUDA;
+  }
+  d.theta_s = ths;
+  d.hksat = hks;
+  d.bsw = bs;
+  d.psi_s = ps;
+  d.fmax = fm;
+  CK(cudaMemset(d.first_key, 0xFF, sizeof(unsigned long long)));
+  std::vector<float> h;
+  /* padding cells get a benign copy of the last land cell's parameters */
+  auto up8 = [&](const float* src, float* dst) -> int {
+    gather(ctx, src, NL, NL, h);
+    for (int k = d.nc; k < d.ncs && d.nc > 0; ++k)
+      for (int i = 0; i < NL; ++i) h[(size_t)k * NL + i] = h[(size_t)(d.nc - 1) * NL + i];
+    return upload(ctx, dst, h);
+  };
+  if (up8(theta_s, ths) || up8(hksat, hks) || up8(bsw, bs) || up8(psi_s, ps)) return H9_ERR_CUDA;
+  gather(ctx, fmax, 1, 1, h);
+  if (upload(ctx, fm, h)) return H9_ERR_CUDA;
+  std::vector<int32_t> xy((size_t)d.ncs, d.nc > 0 ? ctx->cell_xy[d.nc - 1] : 0);
+  std::copy(ctx->cell_xy.begin(), ctx->cell_xy.end(), xy.begin());
+  if (upload(ctx, ctx->d_cell_xy, xy)) return H9_ERR_CUDA;
+  ctx->have_soil = true;
+  return H9_OK;
+}
+
+int64_t h9_num_land(const h9_ctx* ctx) { return (ctx && ctx->have_soil) ? ctx->dev.nc : -1; }
+
+int h9_get_land_index(const h9_ctx* ctx, int32_t* cell_xy) {
+  if (!ctx || !ctx->have_soil || !cell_xy) return H9_ERR_ARG;
+  std::copy(ctx->cell_xy.begin(), ctx->cell_xy.end(), cell_xy);
+  return H9_OK;
+}
+
+int h9_set_state(h9_ctx* ctx, const float* h2osoi_liq, const float* zwt, const float* wa,
+                 const float* lai, const float* lai_litter, const float* plant_mass,
+                 const float* plant_foliage_mass, const float* plant_length, const float* rdepth,
+                 const float* rootr_col, const int32_t* nplants, const float* smp) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_set_state: call h9_set_soil first");
+  if (!h2osoi_liq || !zwt || !wa || !lai || !lai_litter || !plant_mass || !plant_foliage_mass ||
+      !plant_length || !rdepth || !rootr_col || !nplants)
+    return fail(ctx, H9_ERR_ARG, "h9_set_state: null pointer");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  DevArrays& d = ctx->dev;
+  std::vector<float> h;
+  gather(ctx, h2osoi_liq, NL, NL, h);
+  if (upload(ctx, d.h2o, h)) return H9_ERR_CUDA;
+  gather(ctx, rootr_col, 9, NL, h); /* rootr_col(9,...) : element 9 is always 0 (GROW.f90:76) */
+  if (upload(ctx, d.rootr, h)) return H9_ERR_CUDA;
+  if (smp) {
+    gather(ctx, smp, NL, NL, h);
+  } else {
+    h.assign((size_t)d.ncs * NL, 0.0f); /* INIT.f90:109 leaves smp undefined; we define it as 0 */
+  }
+  if (upload(ctx, d.smp, h)) return H9_ERR_CUDA;
+  struct {
+    const float* src;
+    float* dst;
+  } sc[] = {{zwt, d.zwt},
+            {wa, d.wa},
+            {lai, d.lai},
+            {lai_litter, d.lai_litter},
+            {plant_mass, d.plant_mass},
+            {plant_foliage_mass, d.plant_foliage_mass},
+            {plant_length, d.plant_length},
+            {rdepth, d.rdepth}};
+  for (auto& e : sc) {
+    gather(ctx, e.src, 1, 1, h);
+    if (upload(ctx, e.dst, h)) return H9_ERR_CUDA;
+  }
+  std::vector<int32_t> hi;
+  gather(ctx, nplants, 1, 1, hi);
+  if (upload(ctx, d.nplants, hi)) return H9_ERR_CUDA;
+  return H9_OK;
+}
+
+int h9_get_state(h9_ctx* ctx, float* h2osoi_liq, float* zwt, float* wa, float* lai,
+                 float* lai_litter, float* plant_mass, float* plant_foliage_mass,
+                 float* plant_length, float* rdepth, float* rootr_col, int32_t* nplants, float* smp) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_get_state: no state");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  DevArrays& d = ctx->dev;
+  const size_t n = (size_t)d.ncs;
+  std::vector<float> h;
+  if (h2osoi_liq) {
+    if (download(ctx, h, d.h2o, n * NL)) return H9_ERR_CUDA;
+    scatter(ctx, h.data(), NL, NL, h2osoi_liq);
+  }
+  if (smp) {
+    if (download(ctx, h, d.smp, n * NL)) return H9_ERR_CUDA;
+    scatter(ctx, h.data(), NL, NL, smp);
+  }
+  if (rootr_col) {
+    if (download(ctx, h, d.rootr, n * NL)) return H9_ERR_CUDA;
+    scatter(ctx, h.data(), NL, 9, rootr_col);
+    for (int k = 0; k < d.nc; ++k) rootr_col[(size_t)ctx->cell_xy[k] * 9 + 8] = 0.0f;
+  }
+  struct {
+    float* dst;
+    const float* src;
+  } sc[] = {{zwt, d.zwt},
+            {wa, d.wa},
+            {lai, d.lai},
+            {lai_litter, d.lai_litter},
+            {plant_mass, d.plant_mass},
+            {plant_foliage_mass, d.plant_foliage_mass},
+            {plant_length, d.plant_length},
+            {rdepth, d.rdepth}};
+  for (auto& e : sc) {
+    if (!e.dst) continue;
+    if (download(ctx, h, e.src, n)) return H9_ERR_CUDA;
+    scatter(ctx, h.data(), 1, 1, e.dst);
+  }
+  if (nplants) {
+    std::vector<int32_t> hi;
+    if (download(ctx, hi, (const int32_t*)d.nplants, n)) return H9_ERR_CUDA;
+    scatter(ctx, hi.data(), 1, 1, nplants);
+  }
+  return H9_OK;
+}
+
+int h9_run_days_device(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day,
+                       const float* d_forcing, size_t day_stride, size_t plane_stride) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_run_days_device: no soil/state");
+  if (ndays < 0 || !year_index_of_day || !d_forcing)
+    return fail(ctx, H9_ERR_ARG, "h9_run_days_device: bad argument");
+  if (ndays == 0) return H9_OK;
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  if (upload_year_index(ctx, ndays, year_index_of_day)) return H9_ERR_CUDA;
+  if (launch_days(ctx, ndays, ctx->d_year_index, d_forcing, day_stride, plane_stride))
+    return H9_ERR_CUDA;
+  advance_years(ctx, ndays, year_index_of_day);
+  uint32_t any = 0;
+  if (read_any_fault(ctx, &any)) return H9_ERR_CUDA;
+  return (int)any;
+}
+
+int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const float* tas,
+                const float* rlds, const float* rsds, const float* huss, const float* ps,
+                const float* pr, const float* rhs) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_run_days: no soil/state");
+  if (ndays < 0 || !year_index_of_day || !tas || !rlds || !rsds || !huss || !ps || !pr || !rhs)
+    return fail(ctx, H9_ERR_ARG, "h9_run_days: bad argument");
+  if (ndays == 0) return H9_OK;
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const float* src[7] = {tas, rlds, rsds, huss, ps, pr, rhs};
+  bool pinned = true;
+  for (int p = 0; p < 7; ++p) pinned = pinned && is_pinned(src[p]);
+  if (ensure_stage(ctx, !pinned)) return H9_ERR_CUDA;
+  if (upload_year_index(ctx, ndays, year_index_of_day)) return H9_ERR_CUDA;
+  const size_t day_stride = (size_t)kForcingPlanes * ctx->dev.ncs;
+  const int td = ctx->tile_days;
+  const int ntiles = (ndays + td - 1) / td;
+  /* two-deep pipeline: tile k+1 is copied and packed on the copy stream while
+   * tile k is stepped on the compute stream */
+  for (int k = 0; k < ntiles; ++k) {
+    const int b = k & 1;
+    const int d0 = k * td, nd = std::min(td, ndays - d0);
+    if (k >= 2) {
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+      if (!pinned) CK(cudaEventSynchronize(ctx->ev_h2d[b])); /* h_stage[b] is free again */
+    }
+    if (stage_and_pack(ctx, b, d0, nd, src, pinned, ctx->d_packed[b])) return H9_ERR_CUDA;
+    CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
+    if (launch_days(ctx, nd, ctx->d_year_index + d0, ctx->d_packed[b], day_stride,
+                    (size_t)ctx->dev.ncs))
+      return H9_ERR_CUDA;
+    CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    advance_years(ctx, nd, year_index_of_day + d0);
+  }
+  uint32_t any = 0;
+  if (read_any_fault(ctx, &any)) return H9_ERR_CUDA;
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  return (int)any;
+}
+
+int h9_pack_forcing(h9_ctx* ctx, int ndays, const float* tas, const float* rlds,
+                    const float* rsds, const float* huss, const float* ps, const float* pr,
+                    const float* rhs, const float** d_forcing, size_t* day_stride,
+                    size_t* plane_stride) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_pack_forcing: no soil");
+  if (ndays < 1 || !tas || !rlds || !rsds || !huss || !ps || !pr || !rhs || !d_forcing)
+    return fail(ctx, H9_ERR_ARG, "h9_pack_forcing: bad argument");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const float* src[7] = {tas, rlds, rsds, huss, ps, pr, rhs};
+  bool pinned = true;
+  for (int p = 0; p < 7; ++p) pinned = pinned && is_pinned(src[p]);
+  if (ensure_stage(ctx, !pinned)) return H9_ERR_CUDA;
+  const size_t dstride = (size_t)kForcingPlanes * ctx->dev.ncs;
+  const size_t need = (size_t)ndays * dstride;
+  if (need > ctx->pack_full_cap) {
+    if (ctx->d_pack_full) cudaFree(ctx->d_pack_full);
+    ctx->d_pack_full = nullptr;
+    ctx->pack_full_cap = 0;
+    cudaError_t e = cudaMalloc((void**)&ctx->d_pack_full, need * sizeof(float));
+    if (e != cudaSuccess) return fail(ctx, H9_ERR_NOMEM, "h9_pack_forcing: out of device memory");
+    ctx->pack_full_cap = need;
+  }
+  const int td = ctx->tile_days;
+  for (int d0 = 0, k = 0; d0 < ndays; d0 += td, ++k) {
+    const int b = k & 1;
+    const int nd = std::min(td, ndays - d0);
+    if (k >= 2) CK(cudaEventSynchronize(ctx->ev_packed[b])); /* stage b consumed */
+    if (stage_and_pack(ctx, b, d0, nd, src, pinned, ctx->d_pack_full + (size_t)d0 * dstride))
+      return H9_ERR_CUDA;
+    CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
+  }
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  *d_forcing = ctx->d_pack_full;
+  if (day_stride) *day_stride = dstride;
+  if (plane_stride) *plane_stride = (size_t)ctx->dev.ncs;
+  return H9_OK;
+}
+
+int h9_get_annual(h9_ctx* ctx, int iyr, float* axy_npp, float* axy_plant_mass, float* axy_rnf,
+                  float* axy_evap, float* axy_theta_total, float* axy_theta) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_get_annual: no state");
+  if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_get_annual: iyr out of range");
+  if (iyr > ctx->max_year_seen) return H9_OK; /* year not reached: leave the caller's fill values */
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const DevArrays& d = ctx->dev;
+  const size_t n = (size_t)d.ncs;
+  std::vector<float> h;
+  if (download(ctx, h, (const float*)d.annual + (size_t)(iyr - 1) * kAnnualPlanes * n, kAnnualPlanes * n))
+    return H9_ERR_CUDA;
+  float* dst[5] = {axy_npp, axy_plant_mass, axy_rnf, axy_evap, axy_theta_total};
+  for (int k = 0; k < d.nc; ++k) {
+    const size_t ci = (size_t)ctx->cell_xy[k];
+    for (int p = 0; p < 5; ++p)
+      if (dst[p]) dst[p][ci] = h[(size_t)p * n + k];
+    if (axy_theta)
+      for (int i = 0; i < NL; ++i) axy_theta[ci * NL + i] = h[(size_t)(5 + i) * n + k];
+  }
+  return H9_OK;
+}
+
+int h9_annual_device(h9_ctx* ctx, int iyr, const float** d_means, size_t* plane_stride,
+                     const double** d_budget) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_annual_device: no state");
+  if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_annual_device: iyr out of range");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const size_t n = (size_t)ctx->dev.ncs;
+  if (d_means) *d_means = ctx->dev.annual + (size_t)(iyr - 1) * kAnnualPlanes * n;
+  if (plane_stride) *plane_stride = n;
+  if (d_budget) {
+    CKL(launch_budget(ctx->stream, ctx->dev, iyr, ctx->d_budget));
+    *d_budget = ctx->d_budget;
+  }
+  return H9_OK;
+}
+
+int h9_get_fault(h9_ctx* ctx, h9_fault* out) {
+  if (!ctx || !out) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_get_fault: no state");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  memset(out, 0, sizeof(*out));
+  const DevArrays& d = ctx->dev;
+  std::vector<uint32_t> f;
+  if (download(ctx, f, (const uint32_t*)d.fault, (size_t)d.nc)) return H9_ERR_CUDA;
+  for (int k = 0; k < d.nc; ++k)
+    if (f[k]) {
+      out->any |= f[k];
+      out->n_faulted += 1;
+    }
+  if (!out->any) return H9_OK;
+  unsigned long long key = 0;
+  CK(cudaMemcpy(&key, d.first_key, sizeof(key), cudaMemcpyDeviceToHost));
+  const unsigned cell = (unsigned)(key & 0xFFFFFFFFull);
+  if (key == ~0ull || (int)cell >= d.nc) return H9_OK;
+  unsigned long long step = 0;
+  CK(cudaMemcpy(&out->code, d.first_code + cell, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&step, d.first_step + cell, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&out->imbalance, d.first_imb + cell, 4, cudaMemcpyDeviceToHost));
+  ctx->d2h += 24;
+  const int32_t ci = ctx->cell_xy[cell];
+  out->x = ci % ctx->lon_c + 1;
+  out->y = ci / ctx->lon_c + 1;
+  out->day = (int32_t)(step / (unsigned long long)ctx->nisurf) + 1;
+  out->substep = (int32_t)(step % (unsigned long long)ctx->nisurf) + 1;
+  return H9_OK;
+}
+
+int h9_clear_fault(h9_ctx* ctx) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return H9_OK;
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const DevArrays& d = ctx->dev;
+  CK(cudaMemsetAsync(d.fault, 0, (size_t)d.ncs * 4, ctx->stream));
+  CK(cudaMemsetAsync(d.any_fault, 0, 4, ctx->stream));
+  CK(cudaMemsetAsync(d.first_key, 0xFF, 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return H9_OK;
+}
+
+void* h9_stream(h9_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int h9_synchronize(h9_ctx* ctx) {
+  if (!ctx) return H9_ERR_ARG;
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return H9_OK;
+}
+
+void* h9_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void h9_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int64_t h9_launch_count(const h9_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int64_t h9_h2d_bytes(const h9_ctx* ctx) { return ctx ? ctx->h2d : -1; }
+int64_t h9_d2h_bytes(const h9_ctx* ctx) { return ctx ? ctx->d2h : -1; }
+
+double h9_step_kernel_ms(h9_ctx* ctx) {
+  if (!ctx) return -1.0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& pr : ctx->timing) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) ctx->step_ms += ms;
+    ctx->event_pool.push_back(pr.first);
+    ctx->event_pool.push_back(pr.second);
+  }
+  ctx->timing.clear();
+  return ctx->step_ms;
+}
+
+int h9_reset_counters(h9_ctx* ctx) {
+  if (!ctx) return H9_ERR_ARG;
+  h9_step_kernel_ms(ctx);
+  ctx->step_ms = 0.0;
+  ctx->launches = ctx->h2d = ctx->d2h = 0;
+  return H9_OK;
+}
+
+int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const float* rsds,
+                      const float* huss, const float* ps, const float* pr, const float* rhs,
+                      float* theta, float* qflx_tran_veg_col, float* qflx_evap_grnd,
+                      float* rnf_inc, float* w_imbalance, int32_t* jwt) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_hydrology_step: no soil/state");
+  if (!tas || !rlds || !rsds || !huss || !ps || !pr || !rhs)
+    return fail(ctx, H9_ERR_ARG, "h9_hydrology_step: null forcing");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const DevArrays& d = ctx->dev;
+  const size_t n = (size_t)d.ncs;
+  const float* src[7] = {tas, rlds, rsds, huss, ps, pr, rhs};
+  std::vector<float> h(n * kForcingPlanes, 0.0f);
+  for (int p = 0; p < 7; ++p)
+    for (int k = 0; k < d.nc; ++k) h[(size_t)p * n + k] = src[p][ctx->cell_xy[k]];
+  if (upload(ctx, ctx->d_step_forcing, h)) return H9_ERR_CUDA;
+  StepDiagArrays diag;
+  diag.theta = ctx->d_diag;
+  diag.qflx_tran_veg_col = ctx->d_diag + 8 * n;
+  diag.qflx_evap_grnd = ctx->d_diag + 9 * n;
+  diag.rnf_inc = ctx->d_diag + 10 * n;
+  diag.w_imbalance = ctx->d_diag + 11 * n;
+  diag.jwt = (int32_t*)(ctx->d_diag + 12 * n);
+  if (ctx->math_mode == H9_MATH_EXACT) {
+    CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, ctx->d_step_forcing, n,
+                                    ctx->step_counter, diag));
+  } else {
+    CKL(launch_hydrology_step_fast(ctx->stream, d, ctx->geo, ctx->d_step_forcing, n,
+                                   ctx->step_counter, diag));
+  }
+  ctx->step_counter += 1;
+  std::vector<float> o;
+  if (download(ctx, o, (const float*)ctx->d_diag, n * 13)) return H9_ERR_CUDA;
+  if (theta) scatter(ctx, o.data(), NL, NL, theta);
+  float* dst[4] = {qflx_tran_veg_col, qflx_evap_grnd, rnf_inc, w_imbalance};
+  for (int q = 0; q < 4; ++q)
+    if (dst[q]) scatter(ctx, o.data() + (8 + q) * n, 1, 1, dst[q]);
+  if (jwt) scatter(ctx, (const int32_t*)(o.data() + 12 * n), 1, 1, jwt);
+  uint32_t any = 0;
+  if (read_any_fault(ctx, &any)) return H9_ERR_CUDA;
+  return (int)any;
+}
+
+int h9_grow_day(h9_ctx* ctx, const float* tas, float* npp, float* w_i, float* fT) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_grow_day: no soil/state");
+  if (!tas) return fail(ctx, H9_ERR_ARG, "h9_grow_day: null tas");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const DevArrays& d = ctx->dev;
+  const size_t n = (size_t)d.ncs;
+  std::vector<float> h(n, 0.0f);
+  for (int k = 0; k < d.nc; ++k) h[k] = tas[ctx->cell_xy[k]];
+  if (upload(ctx, ctx->d_step_forcing, h)) return H9_ERR_CUDA;
+  GrowDiagArrays diag;
+  diag.npp = ctx->d_diag;
+  diag.w_i = ctx->d_diag + n;
+  diag.fT = ctx->d_diag + 2 * n;
+  if (ctx->math_mode == H9_MATH_EXACT) {
+    CKL(launch_grow_day_exact(ctx->stream, d, ctx->geo, ctx->d_step_forcing, diag));
+  } else {
+    CKL(launch_grow_day_fast(ctx->stream, d, ctx->geo, ctx->d_step_forcing, diag));
+  }
+  std::vector<float> o;
+  if (download(ctx, o, (const float*)ctx->d_diag, n * 3)) return H9_ERR_CUDA;
+  if (npp) scatter(ctx, o.data(), 1, 1, npp);
+  if (w_i) scatter(ctx, o.data() + n, 1, 1, w_i);
+  if (fT) scatter(ctx, o.data() + 2 * n, 1, 1, fT);
+  return H9_OK;
+}
+
+int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const float* theta_s,
+                           int nranks, int32_t* lat_s, int32_t* lat_count, int64_t* n_land) {
+  if (lon_c < 1 || lat_c < 1 || !soil_tex || !theta_s || nranks < 1 || !lat_s || !lat_count)
+    return H9_ERR_ARG;
+  std::vector<int64_t> row(lat_c, 0);
+  int64_t total = 0;
+  for (int y = 0; y < lat_c; ++y) {
+    for (int x = 0; x < lon_c; ++x) {
+      const size_t ci = (size_t)y * lon_c + x;
+      volatile float sum = 0.0f;
+      for (int i = 0; i < NL; ++i) sum = sum + theta_s[ci * NL + i];
+      if (soil_tex[ci] > 0 && soil_tex[ci] != 13 && sum > 1.0E-8f) row[y] += 1;
+    }
+    total += row[y];
+  }
+  /* greedy prefix split: band r ends at the first row where the running count
+   * reaches (r+1)/nranks of the land cells; every band keeps >= 0 rows and the
+   * bands tile [1, lat_c] in order (north to south, INIT.f90:145) */
+  int y = 0;
+  int64_t run = 0;
+  for (int r = 0; r < nranks; ++r) {
+    const int y0 = y;
+    int64_t mine = 0;
+    const int64_t target = (total * (r + 1) + nranks - 1) / nranks;
+    if (r == nranks - 1) {
+      while (y < lat_c) mine += row[y++];
+    } else {
+      while (y < lat_c && run + mine < target) {
+        /* stop before a row that would overshoot more than it undershoots */
+        const int64_t after = run + mine + row[y];
+        if (after > target && (after - target) > (target - (run + mine)) && mine > 0) break;
+        mine += row[y++];
+      }
+    }
+    run += mine;
+    lat_s[r] = y0 + 1;
+    lat_count[r] = y - y0;
+    if (n_land) n_land[r] = mine;
+  }
+  return H9_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,211 @@
+/*
+ * h9gpu.h -- C ABI of libh9gpu, the B200-native replacement for HYBRID9's
+ * per-grid-cell time-stepping hot path.
+ *
+ * What this boundary replaces (all citations relative to /root/reference/SOURCE):
+ *
+ *   The reference has no operator/plugin API: HYDROLOGY (HYDROLOGY.f90:2) and
+ *   GROW (GROW.f90:2) are argument-less subroutines that work on the module
+ *   globals of SHARED/CONTROL for ONE cell and ONE step, called from the
+ *   6-deep loop nest of PROGRAM H9 (HYBRID9.f90:120-295, calls at :203 and
+ *   :217).  A GPU needs all cells per step, so the drop-in boundary is that
+ *   loop nest: the Fortran host keeps CONTROL/INIT/SHARED, driver.txt,
+ *   READ_PGF and the WRITE_NET_CDF_* writers, and replaces the body of its
+ *   decade loop by the calls below (see INTEGRATION.md for the ISO_C_BINDING
+ *   interface module).
+ *
+ * Array conventions: every host pointer is the dense data of the Fortran
+ * array named in the comment, column-major, exactly as the reference holds
+ * it (C_LOC of the allocatable).  (8,lon_c,lat_c) means layer fastest.
+ * lat index 1 is the northernmost row of the block (INIT.f90:145).
+ * The caller owns all host pointers; the library copies what it needs
+ * before returning.  One h9_ctx drives one GPU and is used by one host
+ * thread (one MPI rank in the reference's 1-rank-per-block layout).
+ *
+ * Return value: 0 on success; >0 = a physics fault of the kind that makes the
+ * reference STOP (see h9_fault); <0 = usage/CUDA error, text via
+ * h9_last_error().
+ */
+#ifndef H9GPU_H
+#define H9GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h9_ctx h9_ctx;
+
+#define H9_NLAYERS 8 /* nsoil_layers_max, SHARED.f90:294 */
+#define H9_NLEVGRND 9 /* Nlevgrnd, SHARED.f90:300 */
+
+/* error codes (<0) */
+#define H9_OK 0
+#define H9_ERR_ARG -1
+#define H9_ERR_CUDA -2
+#define H9_ERR_STATE -3
+#define H9_ERR_NOMEM -4
+
+/* fault bits: the four conditions on which the reference STOPs */
+#define H9_FAULT_TRIDIAG_PIVOT1 1u  /* bmx(1)==0      HYDROLOGY.f90:806-812  */
+#define H9_FAULT_TRIDIAG_PIVOT2 2u  /* BET==0         HYDROLOGY.f90:818-825  */
+#define H9_FAULT_RSUB_POSITIVE 4u   /* rsub_top_tot>0 HYDROLOGY.f90:1068-1071 */
+#define H9_FAULT_WATER_IMBALANCE 8u /* |w1-w0|>0.1    HYDROLOGY.f90:1244-1274 */
+
+/* arithmetic mode of the device kernels */
+#define H9_MATH_EXACT 0 /* IEEE div, no FMA contraction, CUDA powf/expf: follows the Fortran op for op */
+#define H9_MATH_FAST 1  /* FMA contraction, shared reciprocals, in-house positive-domain pow (default) */
+
+typedef struct h9_fault {
+  uint32_t any;       /* OR of the fault bits over all cells since the last clear */
+  uint32_t code;      /* fault bits of the FIRST fault (earliest step, lowest cell) */
+  int32_t x, y;       /* 1-based block indices of that cell, as in the reference's messages */
+  int32_t day;        /* 1-based day since the ctx was created/reset (DiTIME analogue) */
+  int32_t substep;    /* 1-based NS within the day */
+  float imbalance;    /* w1-w0 (mm) of that step, for the "Water imbalance" message */
+  int64_t n_faulted;  /* number of cells with a non-zero sticky fault word */
+} h9_fault;
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* device_id < 0: use the current CUDA device. */
+int h9_create(h9_ctx** ctx, int device_id);
+int h9_destroy(h9_ctx* ctx);
+const char* h9_last_error(const h9_ctx* ctx);
+
+/* lon_c, lat_c: block shape (CONTROL.f90:49-50, INIT.f90:274-283);
+ * nisurf: sub-steps per day (driver.txt:2, dt = 86400/NISURF INIT.f90:214);
+ * zi[0..9]: layer interfaces in mm (driver.txt:17-26, INIT.f90:202-204);
+ * nyr: number of years the annual diagnostics must hold (NYR, INIT.f90:286-290). */
+int h9_configure(h9_ctx* ctx, int lon_c, int lat_c, int nisurf, const float zi[10], int nyr);
+
+/* H9_MATH_EXACT or H9_MATH_FAST; may be switched between runs. */
+int h9_set_math(h9_ctx* ctx, int mode);
+
+/* Tuning knobs with no effect on results: days of forcing per pipeline tile of
+ * h9_run_days (default 8, env H9_TILE_DAYS) and threads per block of the
+ * time-stepping kernel (32, 64 or 128; default 64, env H9_BLOCK). <=0 keeps. */
+int h9_set_tuning(h9_ctx* ctx, int tile_days, int block);
+
+/* soil_tex (lon_c,lat_c) int32; theta_s,hksat,bsw,psi_s (8,lon_c,lat_c); fmax (lon_c,lat_c).
+ * Builds the land mask with the reference's predicate and iteration order
+ * (HYBRID9.f90:120-123) and uploads the compacted parameters. */
+int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, const float* hksat,
+                const float* bsw, const float* psi_s, const float* fmax);
+
+/* number of land cells found by h9_set_soil; cell_xy (optional, n entries)
+ * receives (y-1)*lon_c+(x-1) of each land cell in compact order. */
+int64_t h9_num_land(const h9_ctx* ctx);
+int h9_get_land_index(const h9_ctx* ctx, int32_t* cell_xy);
+
+/* State as INIT.f90:707-811 leaves it (or as a previous h9_get_state returned it):
+ * h2osoi_liq (8,lon_c,lat_c); zwt, wa, lai, lai_litter (lon_c,lat_c);
+ * plant_mass, plant_foliage_mass, plant_length, rdepth (1,lon_c,lat_c);
+ * rootr_col (9,lon_c,lat_c); nplants (lon_c,lat_c) int32;
+ * smp (8,lon_c,lat_c) or NULL => zeros (the reference leaves smp uninitialised,
+ * INIT.f90:109; see DESIGN.md "smp").  Only land cells are read/written. */
+int h9_set_state(h9_ctx* ctx, const float* h2osoi_liq, const float* zwt, const float* wa,
+                 const float* lai, const float* lai_litter, const float* plant_mass,
+                 const float* plant_foliage_mass, const float* plant_length, const float* rdepth,
+                 const float* rootr_col, const int32_t* nplants, const float* smp);
+int h9_get_state(h9_ctx* ctx, float* h2osoi_liq, float* zwt, float* wa, float* lai,
+                 float* lai_litter, float* plant_mass, float* plant_foliage_mass,
+                 float* plant_length, float* rdepth, float* rootr_col, int32_t* nplants, float* smp);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* Replaces HYBRID9.f90:120-295 for `ndays` consecutive days: for every land
+ * cell, per day: forcing derivation (:156-190), NISURF x HYDROLOGY (:193-211),
+ * GROW (:217), daily/annual accumulators (:235-254).
+ * year_index_of_day[d] = iY (1-based year within the run, HYBRID9.f90:269) of day d;
+ * tas,rlds,rsds,huss,ps,pr,rhs: (lon_c,lat_c,ndays) exactly as READ_PGF leaves them.
+ * Host pointers may be pageable or pinned (h9_host_alloc); pinned is faster.
+ * Returns 0, or >0 (fault bits) if any cell faulted -- the caller then reads
+ * h9_get_fault and STOPs like the reference. */
+int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const float* tas,
+                const float* rlds, const float* rsds, const float* huss, const float* ps,
+                const float* pr, const float* rhs);
+
+/* Same, with forcing already device-resident in compact form: 7 arrays
+ * [ndays][ncell_stride] (day-major, land cells in compact order).  Used by
+ * bench.py's kernel-only `value` and by multi-decade runs that keep a forcing
+ * ring on the device. Order of the 7 planes: tas,rlds,rsds,huss,ps,pr,rhs. */
+int h9_run_days_device(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day,
+                       const float* d_forcing, size_t day_stride, size_t plane_stride);
+
+/* Pack (lon_c,lat_c,ndays) host forcing into the compact device layout that
+ * h9_run_days_device consumes (land compaction + transpose on the GPU). The
+ * returned device pointer is owned by the ctx and valid until the next pack. */
+int h9_pack_forcing(h9_ctx* ctx, int ndays, const float* tas, const float* rlds,
+                    const float* rsds, const float* huss, const float* ps, const float* pr,
+                    const float* rhs, const float** d_forcing, size_t* day_stride,
+                    size_t* plane_stride);
+
+/* Annual means of year iyr (1-based) as HYBRID9.f90:263-291 computes them.
+ * axy_npp, axy_plant_mass, axy_rnf, axy_evap, axy_theta_total: (lon_c,lat_c);
+ * axy_theta: (8,lon_c,lat_c).  Only land cells are written, so the NaN/0 fill
+ * of INIT.f90:402-414 survives elsewhere.  Any pointer may be NULL. */
+int h9_get_annual(h9_ctx* ctx, int iyr, float* axy_npp, float* axy_plant_mass, float* axy_rnf,
+                  float* axy_evap, float* axy_theta_total, float* axy_theta);
+
+/* Compact device-side view of the same means for collectives (no host copy):
+ * 13 planes [13][ncell_stride] in the order npp, plant_mass, rnf, evap,
+ * theta_total, theta(1..8); plus 8 FP64 budget partial sums over the cells of
+ * this ctx: sum of soil water (current h2osoi_liq), sum of wa, sum of annual
+ * rnf, sum of annual npp, sum of annual mean plant_mass, n_cells, sum of annual
+ * mean total soil water, n_faulted.  Pointers are device pointers valid until
+ * the next call; the work is stream-ordered on h9_stream().  The budget is new
+ * (the reference has no global reduction); it is FP64 because its summation
+ * order depends on the shard count. */
+int h9_annual_device(h9_ctx* ctx, int iyr, const float** d_means, size_t* plane_stride,
+                     const double** d_budget);
+
+int h9_get_fault(h9_ctx* ctx, h9_fault* out);
+int h9_clear_fault(h9_ctx* ctx);
+
+/* CUDA stream (cudaStream_t) the ctx launches on, and a full synchronize. */
+void* h9_stream(h9_ctx* ctx);
+int h9_synchronize(h9_ctx* ctx);
+
+/* Pinned host memory for forcing arrays (Fortran side: C_F_POINTER on the result). */
+void* h9_host_alloc(size_t bytes);
+void h9_host_free(void* p);
+
+/* counters for the bench: kernels launched / bytes copied by this ctx so far */
+int64_t h9_launch_count(const h9_ctx* ctx);
+int64_t h9_h2d_bytes(const h9_ctx* ctx);
+int64_t h9_d2h_bytes(const h9_ctx* ctx);
+/* device time (ms) spent in the time-stepping kernel since the last reset, by
+ * CUDA events on the launching stream; and reset. */
+double h9_step_kernel_ms(h9_ctx* ctx);
+int h9_reset_counters(h9_ctx* ctx);
+
+/* ---- fine-grained entries (1:1 parity targets for the two routines) ---- */
+
+/* One HYDROLOGY sub-step (HYDROLOGY.f90:141-1283) for all land cells with the
+ * given day's forcing, (lon_c,lat_c) each.  Optional outputs (lon_c,lat_c)
+ * unless noted: theta (8,lon_c,lat_c), qflx_tran_veg_col, qflx_evap_grnd,
+ * rnf_inc ((qflx_surf+rsub_top)*dt), w_imbalance (w1-w0), jwt (int32, the
+ * value after Drainage). */
+int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const float* rsds,
+                      const float* huss, const float* ps, const float* pr, const float* rhs,
+                      float* theta, float* qflx_tran_veg_col, float* qflx_evap_grnd,
+                      float* rnf_inc, float* w_imbalance, int32_t* jwt);
+
+/* One GROW call (GROW.f90:55-201) for all land cells; tas (lon_c,lat_c).
+ * Optional outputs (lon_c,lat_c): npp, w_i, fT. */
+int h9_grow_day(h9_ctx* ctx, const float* tas, float* npp, float* w_i, float* fT);
+
+/* Balanced contiguous latitude bands for `nranks` ranks: rows are assigned so
+ * that every band holds about the same number of land cells (the reference's
+ * INIT.f90:271-283 uses equal-area squares instead).  lat_s[r] is 1-based,
+ * lat_c[r] the row count.  Pure host function, no ctx needed. */
+int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const float* theta_s,
+                           int nranks, int32_t* lat_s, int32_t* lat_count, int64_t* n_land);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H9GPU_H */
