@@ -69,9 +69,16 @@ def grid_spec(name):
     if name == "0.25":
         return dict(nx=1440, ny=720, n_land=269680, label="0.25deg global land mask")
     if name == "regional":
-        return dict(nx=720, ny=360, n_land=67420, label="regional 100x74 window of the 0.5deg mask",
-                    window=(340, 37, 100, 74))
+        # SURVEY.md 8d names a 100x74 window at (lon_s=340, lat_s=37) ("Europe"); the synthetic
+        # continents are not Earth's, so the window is placed where it holds 2,500 land cells
+        return dict(nx=720, ny=360, n_land=67420, label="regional 100x74 window of the 0.5deg mask "
+                    "(2,500 land cells)", window=synth_regional_window())
     return dict(nx=72, ny=36, n_land=674, label="tiny 5deg test grid")
+
+
+def synth_regional_window():
+    from hybrid9_b200 import synth
+    return synth.REGIONAL_WINDOW
 
 
 def peaks():

@@ -20,8 +20,9 @@
  *
  * The arithmetic policy M supplies pow/exp/log/div: MathExact keeps the
  * reference's operation order with IEEE division (its translation unit is
- * built with -fmad=false), MathFast uses MUFU ex2/lg2/rcp and lets the
- * compiler contract multiply-adds.
+ * built with -fmad=false) and computes pow/exp/log with portable double-precision
+ * kernels that give the same bits on the GPU and on a host build; MathFast uses
+ * MUFU ex2/lg2/rcp and lets the compiler contract multiply-adds.
  *
  * The header is plain C++ so that tests/twin can compile the very same source
  * for the host and diff it against the oracle without a GPU.
@@ -29,8 +30,10 @@
 #ifndef H9_PHYSICS_H
 #define H9_PHYSICS_H
 
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define H9_HD __host__ __device__ __forceinline__
@@ -120,13 +123,117 @@ struct StepOut {
 
 /* ---- arithmetic policies ------------------------------------------------ */
 
+/* Portable transcendental kernels for the exact mode: IEEE double +,*,/ and fma
+ * only (no libm, no vendor intrinsics), so that the CUDA kernel and a host
+ * build of this header produce the SAME BITS.  Accuracy: relative error below
+ * 1e-14 before the final rounding to float, i.e. the float result is correctly
+ * rounded except within ~1e-7 ulp of a rounding boundary. */
+H9_HD double h9_bits_to_double(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double d;
+  memcpy(&d, &u, sizeof(d));
+  return d;
+#endif
+}
+H9_HD uint64_t h9_double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t u;
+  memcpy(&u, &d, sizeof(u));
+  return u;
+#endif
+}
+
+/* log2(x) for finite x > 0 that is a normal double (every positive float is) */
+H9_HD double h9_log2_pos(double x) {
+  const uint64_t u = h9_double_to_bits(x);
+  int e = (int)((u >> 52) & 0x7FF) - 1023;
+  double m = h9_bits_to_double((u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull); /* [1,2) */
+  if (m > 1.4142135623730951) {
+    m = m * 0.5;
+    e += 1;
+  }
+  const double f = (m - 1.0) / (m + 1.0); /* |f| <= 0.1716 */
+  const double s = f * f;
+  /* atanh series: ln(m) = 2 f (1 + s/3 + s^2/5 + ... + s^11/23) */
+  double p = 1.0 / 23.0;
+  p = fma(p, s, 1.0 / 21.0);
+  p = fma(p, s, 1.0 / 19.0);
+  p = fma(p, s, 1.0 / 17.0);
+  p = fma(p, s, 1.0 / 15.0);
+  p = fma(p, s, 1.0 / 13.0);
+  p = fma(p, s, 1.0 / 11.0);
+  p = fma(p, s, 1.0 / 9.0);
+  p = fma(p, s, 1.0 / 7.0);
+  p = fma(p, s, 1.0 / 5.0);
+  p = fma(p, s, 1.0 / 3.0);
+  p = fma(p, s, 1.0);
+  const double lnm = 2.0 * f * p;
+  return fma(lnm, 1.4426950408889634, (double)e);
+}
+
+/* 2**y for any double y (saturates far outside the float range) */
+H9_HD double h9_exp2(double y) {
+  if (!(y == y)) return y;
+  if (y > 300.0) y = 300.0;
+  if (y < -300.0) y = -300.0;
+  const double big = 6755399441055744.0; /* 1.5 * 2^52: round-to-nearest-integer trick */
+  const double k = (y + big) - big;
+  const double r = (y - k) * 0.6931471805599453; /* |r| <= 0.3466 */
+  /* exp(r), Taylor to r^13 */
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const uint64_t sc = (uint64_t)((int64_t)k + 1023) << 52; /* 2^k, k in [-300,300] */
+  return p * h9_bits_to_double(sc);
+}
+
 struct MathExact {
   static constexpr bool kFast = false;
-  static H9_HD float pow(float a, float b) { return powf(a, b); }
-  static H9_HD float exp(float a) { return expf(a); }
-  static H9_HD float log(float a) { return logf(a); }
+  /* a**b with Fortran REAL semantics on the domain this path uses (a >= 0) */
+  static H9_HD float pow(float a, float b) {
+    if (b == 0.0f || a == 1.0f) return 1.0f;
+    if (!(a == a) || !(b == b)) return a + b; /* NaN */
+    if (a < 0.0f) return NAN;                 /* negative base, real exponent */
+    if (a == 0.0f) return b > 0.0f ? 0.0f : INFINITY;
+    if (a > FLT_MAX) return b > 0.0f ? a : 0.0f; /* +inf */
+    return (float)h9_exp2((double)b * h9_log2_pos((double)a));
+  }
+  static H9_HD float exp(float a) { return (float)h9_exp2((double)a * 1.4426950408889634); }
+  static H9_HD float log(float a) {
+    if (!(a > 0.0f)) return a == 0.0f ? -INFINITY : NAN;
+    if (a > FLT_MAX) return a;
+    return (float)(h9_log2_pos((double)a) * 0.6931471805599453);
+  }
   static H9_HD float div(float a, float b) { return a / b; }
 };
+
+#if !defined(__CUDACC__)
+/* host-only policy with the C library's powf/expf/logf: what the oracle uses.
+ * tests/twin builds the kernel source with it to diff the LOGIC against the
+ * oracle bit for bit. */
+struct MathLibm {
+  static constexpr bool kFast = false;
+  static inline float pow(float a, float b) { return powf(a, b); }
+  static inline float exp(float a) { return expf(a); }
+  static inline float log(float a) { return logf(a); }
+  static inline float div(float a, float b) { return a / b; }
+};
+#endif
 
 #if defined(__CUDACC__)
 struct MathFast {

@@ -24,6 +24,9 @@ ZI_DRIVER = np.array([0.0, 45.0, 91.0, 166.0, 289.0, 493.0, 829.0, 1383.0, 2296.
 NISURF_DRIVER = 48               # EXECUTE/driver.txt:2
 N_LAND_HALF_DEG = 67420
 N_LAND_QUARTER_DEG = 269680
+# BASELINE.json config 2: a 100x74 regional block (lon_s, lat_s, lon_c, lat_c) of the seed-9
+# 0.5 deg world holding exactly 2,500 land cells
+REGIONAL_WINDOW = (73, 8, 100, 74)
 
 
 @dataclass

@@ -242,14 +242,18 @@ def load_twin():
     lib = C.CDLL(path)
     fp, ip, up = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
     lib.h9t_run.restype = C.c_int
-    lib.h9t_run.argtypes = ([C.c_int, C.c_int, C.c_int, fp] + [fp] * 16 + [ip, fp, fp, C.c_int, up,
+    lib.h9t_run.argtypes = ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp] + [fp] * 16 + [ip, fp, fp, C.c_int, up,
                             fp, fp, fp, fp, ip, fp, fp, fp])
+    for n, a in (("h9t_pow", [C.c_float, C.c_float]), ("h9t_exp", [C.c_float]), ("h9t_log", [C.c_float])):
+        getattr(lib, n).restype = C.c_float
+        getattr(lib, n).argtypes = a
     return lib
 
 
-def twin_run(world, state, forcing, nisurf, zi, do_grow=True):
+def twin_run(world, state, forcing, nisurf, zi, do_grow=True, math="libm", nsteps=-1):
     """Run the host twin of the kernel source over the land cells of `world`.
-    forcing[k]: (ndays, ny, nx).  Returns (H9State, extras dict)."""
+    forcing[k]: (ndays, ny, nx).  nsteps: HYDROLOGY calls per day (-1 = nisurf; dt is
+    always 86400/nisurf).  Returns (H9State, extras dict)."""
     lib = load_twin()
     land = world.land
     yy, xx = np.nonzero(land)
@@ -274,7 +278,7 @@ def twin_run(world, state, forcing, nisurf, zi, do_grow=True):
     dn, dw, dft = (np.zeros((nd, n), np.float32) for _ in range(3))
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
     zi = f(zi)
-    rc = lib.h9t_run(n, nd, nisurf, P(zi), P(comp["h2osoi_liq"]), P(comp["smp"]), P(rootr),
+    rc = lib.h9t_run(0 if math == "libm" else 1, nsteps, n, nd, nisurf, P(zi), P(comp["h2osoi_liq"]), P(comp["smp"]), P(rootr),
                      P(par["theta_s"]), P(par["hksat"]), P(par["bsw"]), P(par["psi_s"]),
                      P(par["fmax"]), P(comp["zwt"]), P(comp["wa"]), P(comp["lai"]),
                      P(comp["lai_litter"]), P(pk["plant_mass"]), P(pk["plant_foliage_mass"]),

@@ -2,7 +2,8 @@
  * h9_twin.cpp -- TEST-ONLY host build of the kernel source.
  *
  * Compiles hybrid9_b200/csrc/h9_physics.h (the exact text the CUDA kernels
- * instantiate) for the CPU with the MathExact policy and -ffp-contract=off, so
+ * instantiate) for the CPU with -ffp-contract=off, once with the libm policy and once with the
+ * portable exact-mode policy, so
  * that the -m "not gpu" suite can diff the kernel's logic against the oracle
  * before any GPU time is spent.  Same libm as the oracle => the two must agree
  * bit for bit; a difference is a logic bug in one of the two restatements.
@@ -15,12 +16,11 @@
 
 using namespace h9;
 
-extern "C" {
-
 /* All per-layer arrays are compact [ncell][8]; forcing is [ndays][7][ncell].
  * State arrays are updated in place. theta_out [ncell][8] gets the end state's
  * diagnostic theta.  daily_* (optional, [ndays][ncell]) get per-day npp, w_i, fT. */
-int h9t_run(int ncell, int ndays, int nisurf, const float* zi, float* h2o, float* smp,
+template <class M>
+static int twin_run(int nsteps, int ncell, int ndays, int nisurf, const float* zi, float* h2o, float* smp,
             float* rootr, const float* theta_s, const float* hksat, const float* bsw,
             const float* psi_s, const float* fmax, float* zwt, float* wa, float* lai,
             float* lai_litter, float* plant_mass, float* plant_foliage_mass, float* plant_length,
@@ -61,11 +61,11 @@ int h9t_run(int ncell, int ndays, int nisurf, const float* zi, float* h2o, float
       Forcing f = {f0[0], f0[(size_t)ncell], f0[(size_t)2 * ncell], f0[(size_t)3 * ncell],
                    f0[(size_t)4 * ncell], f0[(size_t)5 * ncell], f0[(size_t)6 * ncell]};
       Day day;
-      day_setup<MathExact>(g, f, s.lai, s.lai_litter, day);
-      for (int ns = 0; ns < nisurf; ++ns) ft |= hydrology_step<MathExact>(g, p, day, s, so);
+      day_setup<M>(g, f, s.lai, s.lai_litter, day);
+      for (int ns = 0; ns < nsteps; ++ns) ft |= hydrology_step<M>(g, p, day, s, so);
       if (do_grow) {
         GrowOut go;
-        grow_day<MathExact>(g, day.tas, s, go);
+        grow_day<M>(g, day.tas, s, go);
         if (daily_npp) daily_npp[(size_t)d * ncell + c] = go.npp;
         if (daily_wi) daily_wi[(size_t)d * ncell + c] = go.w_i;
         if (daily_ft) daily_ft[(size_t)d * ncell + c] = go.fT;
@@ -75,7 +75,7 @@ int h9t_run(int ncell, int ndays, int nisurf, const float* zi, float* h2o, float
       h2o[c * NL + i] = s.h2o[i];
       smp[c * NL + i] = s.smp[i];
       rootr[c * NL + i] = s.rootr[i];
-      if (theta_out) theta_out[c * NL + i] = theta_diag<MathExact>(g, s.h2o[i], i);
+      if (theta_out) theta_out[c * NL + i] = theta_diag<M>(g, s.h2o[i], i);
     }
     zwt[c] = s.zwt;
     wa[c] = s.wa;
@@ -94,5 +94,36 @@ int h9t_run(int ncell, int ndays, int nisurf, const float* zi, float* h2o, float
   }
   return 0;
 }
+
+extern "C" {
+
+/* math: 0 = MathLibm (the C library's powf/expf/logf, as the oracle), 1 = MathExact
+ * (the portable kernels the GPU's exact mode runs) */
+int h9t_run(int math, int nsteps, int ncell, int ndays, int nisurf, const float* zi, float* h2o, float* smp,
+            float* rootr, const float* theta_s, const float* hksat, const float* bsw,
+            const float* psi_s, const float* fmax, float* zwt, float* wa, float* lai,
+            float* lai_litter, float* plant_mass, float* plant_foliage_mass, float* plant_length,
+            float* rdepth, const int32_t* nplants, float* rnf_sum, const float* forcing,
+            int do_grow, uint32_t* fault, float* theta_out, float* last_tran, float* last_evap,
+            float* last_imb, int32_t* last_jwt, float* daily_npp, float* daily_wi,
+            float* daily_ft) {
+  if (nsteps < 0) nsteps = nisurf; /* HYDROLOGY calls per day; dt stays 86400/nisurf */
+  if (math == 0)
+    return twin_run<MathLibm>(nsteps, ncell, ndays, nisurf, zi, h2o, smp, rootr, theta_s, hksat, bsw, psi_s,
+                              fmax, zwt, wa, lai, lai_litter, plant_mass, plant_foliage_mass,
+                              plant_length, rdepth, nplants, rnf_sum, forcing, do_grow, fault,
+                              theta_out, last_tran, last_evap, last_imb, last_jwt, daily_npp,
+                              daily_wi, daily_ft);
+  return twin_run<MathExact>(nsteps, ncell, ndays, nisurf, zi, h2o, smp, rootr, theta_s, hksat, bsw, psi_s,
+                             fmax, zwt, wa, lai, lai_litter, plant_mass, plant_foliage_mass,
+                             plant_length, rdepth, nplants, rnf_sum, forcing, do_grow, fault,
+                             theta_out, last_tran, last_evap, last_imb, last_jwt, daily_npp,
+                             daily_wi, daily_ft);
+}
+
+/* spot checks of the portable kernels against libm */
+float h9t_pow(float a, float b) { return MathExact::pow(a, b); }
+float h9t_exp(float a) { return MathExact::exp(a); }
+float h9t_log(float a) { return MathExact::log(a); }
 
 } /* extern "C" */
