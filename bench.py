@@ -47,7 +47,7 @@ UNIT = "cell-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])

@@ -34,7 +34,7 @@ struct h9_ctx {
   int lon_c = 0, lat_c = 0, nisurf = 48, nyr = 1;
   size_t ngrid = 0;
   int math_mode = H9_MATH_FAST;
-  int tile_days = 8, block = 64;
+  int tile_days = 8, block = 1064; /* 64 threads/block, 128-register variant */
   Geo geo;
   std::vector<int32_t> cell_xy;
   DevArrays dev;
@@ -313,7 +313,7 @@ int h9_create(h9_ctx** out, int device_id) {
   const char* td = getenv("H9_TILE_DAYS");
   if (td && atoi(td) > 0) ctx->tile_days = atoi(td);
   const char* bl = getenv("H9_BLOCK");
-  if (bl && (atoi(bl) == 32 || atoi(bl) == 64 || atoi(bl) == 128)) ctx->block = atoi(bl);
+  if (bl && (atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
   *out = ctx;
   return H9_OK;
 }
@@ -372,7 +372,7 @@ int h9_set_math(h9_ctx* ctx, int mode) {
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block) {
   if (!ctx) return H9_ERR_ARG;
   if (tile_days > 0) ctx->tile_days = tile_days;
-  if (block == 32 || block == 64 || block == 128) ctx->block = block;
+  if (block % 1000 == 32 || block % 1000 == 64 || block % 1000 == 128) ctx->block = block;
   return H9_OK;
 }
 

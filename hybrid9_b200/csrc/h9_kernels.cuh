@@ -102,8 +102,8 @@ __device__ __forceinline__ void record_fault(const DevArrays& a, int c, uint32_t
   sticky |= code;
 }
 
-template <class M, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+template <class M, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
             const int32_t* __restrict__ year_index, const float* __restrict__ forcing,
             size_t day_stride, size_t plane_stride, int cur_year, int nt,
@@ -248,19 +248,22 @@ int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
                   size_t plane_stride, int cur_year, int nt, unsigned long long step0, int block) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a.nc <= 0 || ndays <= 0) return 0;
-  if (block == 32) {
-    days_kernel<M, 32><<<(a.nc + 31) / 32, 32, 0, st>>>(a, g, ndays, d_year_index, d_forcing,
-                                                        day_stride, plane_stride, cur_year, nt,
-                                                        step0);
-  } else if (block == 128) {
-    days_kernel<M, 128><<<(a.nc + 127) / 128, 128, 0, st>>>(a, g, ndays, d_year_index, d_forcing,
-                                                            day_stride, plane_stride, cur_year,
-                                                            nt, step0);
+  /* block: threads per block (32/64/128) + 1000 when the kernel variant capped at 128
+   * registers per thread (16 warps per SM resident: the whole 0.5 deg grid in one wave) is
+   * wanted instead of the uncapped one (255 registers, 8 warps per SM) */
+  const bool capped = block >= 1000;
+  const int bs = block % 1000;
+#define H9_LAUNCH(BS, MINB)                                                                      \
+  days_kernel<M, BS, MINB><<<(a.nc + BS - 1) / BS, BS, 0, st>>>(                                 \
+      a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0)
+  if (bs == 32) {
+    if (capped) H9_LAUNCH(32, 16); else H9_LAUNCH(32, 1);
+  } else if (bs == 128) {
+    if (capped) H9_LAUNCH(128, 4); else H9_LAUNCH(128, 1);
   } else {
-    days_kernel<M, 64><<<(a.nc + 63) / 64, 64, 0, st>>>(a, g, ndays, d_year_index, d_forcing,
-                                                        day_stride, plane_stride, cur_year, nt,
-                                                        step0);
+    if (capped) H9_LAUNCH(64, 8); else H9_LAUNCH(64, 1);
   }
+#undef H9_LAUNCH
   return (int)cudaGetLastError();
 }
 

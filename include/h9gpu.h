@@ -85,8 +85,10 @@ int h9_configure(h9_ctx* ctx, int lon_c, int lat_c, int nisurf, const float zi[1
 int h9_set_math(h9_ctx* ctx, int mode);
 
 /* Tuning knobs with no effect on results: days of forcing per pipeline tile of
- * h9_run_days (default 8, env H9_TILE_DAYS) and threads per block of the
- * time-stepping kernel (32, 64 or 128; default 64, env H9_BLOCK). <=0 keeps. */
+ * h9_run_days (default 8, env H9_TILE_DAYS) and the launch shape of the
+ * time-stepping kernel: threads per block (32, 64 or 128), plus 1000 to select the
+ * variant compiled for <=128 registers per thread (16 resident warps per SM, so the
+ * 0.5 deg grid runs in one wave).  Default 1064, env H9_BLOCK.  <=0 keeps. */
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block);
 
 /* soil_tex (lon_c,lat_c) int32; theta_s,hksat,bsw,psi_s (8,lon_c,lat_c); fmax (lon_c,lat_c).
