@@ -74,6 +74,11 @@ struct Geo {
   float dzw[10];  /* dz(I)*rhow/1.0E3, HYDROLOGY.f90:148,1234 */
   float dzdt[10]; /* dz(I)/dt, HYDROLOGY.f90:674,700,727 */
   float zi10[10]; /* zi(I)/10, GROW.f90:180-181 */
+  /* reciprocals used by the fast mode only */
+  float rdzw[10]; /* 1/dzw(I) */
+  float rdzl[10]; /* 1/(zi(I)-zi(I-1)) */
+  float rden[10]; /* 1/(zc(I+1)-zc(I)), I = 1..7 */
+  float rdt;      /* 1/dt */
   float dt;
   float q10_lo, q10_hi; /* -10/dt, 10/dt, HYDROLOGY.f90:894-895 */
   int nisurf;
@@ -92,7 +97,11 @@ inline void geo_init(Geo& g, const float zi[10], int nisurf) {
     g.dzw[I] = g.dz[I] * kRhow / 1.0E3f;
     g.dzdt[I] = g.dz[I] / g.dt;
     g.zi10[I] = g.zi[I] / 10.0f;
+    g.rdzw[I] = I >= 1 ? 1.0f / g.dzw[I] : 0.0f;
+    g.rdzl[I] = I >= 1 ? 1.0f / g.dz[I] : 0.0f;
+    g.rden[I] = (I >= 1 && I <= 8) ? 1.0f / (g.zc[I + 1] - g.zc[I]) : 0.0f;
   }
+  g.rdt = 1.0f / g.dt;
   g.q10_lo = -10.0f / g.dt;
   g.q10_hi = 10.0f / g.dt;
 }

@@ -1,0 +1,476 @@
+/*
+ * h9_physics_fast.cuh -- H9_MATH_FAST implementation of one HYDROLOGY sub-step
+ * (HYDROLOGY.f90:141-1283), restructured for the B200's issue and MUFU limits.
+ *
+ * Same algorithm and the same branch semantics as hydrology_step<M> in
+ * h9_physics.h (which follows the Fortran operation by operation); what
+ * changes is the arithmetic around it:
+ *   - every per-cell, per-layer quantity that does not depend on the state
+ *     (1/(-psi_s), 1-1/bsw, psi_s*theta_s/(1-1/bsw)/dz, 1/theta_s, 1/(theta_s(I)+
+ *     theta_s(I+1)), MINVAL(hksat(1:3)) ...) is computed once per launch and kept
+ *     in shared memory, one column per thread (no bank conflicts, no barriers);
+ *   - divisions by geometry or per-day constants are multiplications by
+ *     reciprocals prepared on the host / once per day;
+ *   - pow(a,b) = ex2(b*lg2(a)), exp(x) = ex2(x*log2 e), 1/x = rcp.approx: 2 MUFU
+ *     per pow; the two Cc/Cs fractions of HYDROLOGY.f90:362-366 share one
+ *     denominator; interface fluxes are computed once per interface (the
+ *     reference writes each twice, as qout(I) and qin(I+1));
+ *   - the data-dependent Drainage loops are real loops over the shared-memory
+ *     constants instead of 8-fold predicated unrolls (code size, I-cache).
+ * Results differ from the exact mode at rounding level only; the deviation is
+ * measured against the oracle and the FP32 noise floor in tests/test_gpu_parity.py.
+ */
+#ifndef H9_PHYSICS_FAST_CUH
+#define H9_PHYSICS_FAST_CUH
+
+#include "h9_physics.h"
+
+namespace h9 {
+
+/* rows of the per-cell constant table (each row has NL entries, one per layer) */
+enum FastRow { FR_PSI = 0, FR_INV_NPSI, FR_E1, FR_COEF3, FR_INV_THS, FR_THS, FR_BSW, FR_HKS,
+               FR_INV_THS_SUM, FR_ROOTR, FR_NROWS };
+constexpr int kFastScalars = 2; /* fmax, min(hksat(1:3)) */
+constexpr int kFastFloatsPerCell = FR_NROWS * NL + kFastScalars;
+
+/* one thread's column of the table: element (row, layer) lives at
+ * base[(row*NL + layer) * STRIDE]; STRIDE = threads per block when the table is in
+ * shared memory (consecutive threads -> consecutive banks), 1 for a local array */
+template <int STRIDE>
+struct CellTable {
+  float* base;
+  __device__ __forceinline__ float get(int row, int i) const { return base[(row * NL + i) * STRIDE]; }
+  __device__ __forceinline__ void set(int row, int i, float v) const { base[(row * NL + i) * STRIDE] = v; }
+  __device__ __forceinline__ float psi(int i) const { return get(FR_PSI, i); }
+  __device__ __forceinline__ float inv_npsi(int i) const { return get(FR_INV_NPSI, i); }
+  __device__ __forceinline__ float e1(int i) const { return get(FR_E1, i); }
+  __device__ __forceinline__ float coef3(int i) const { return get(FR_COEF3, i); }
+  __device__ __forceinline__ float inv_ths(int i) const { return get(FR_INV_THS, i); }
+  __device__ __forceinline__ float ths(int i) const { return get(FR_THS, i); }
+  __device__ __forceinline__ float bsw(int i) const { return get(FR_BSW, i); }
+  __device__ __forceinline__ float hks(int i) const { return get(FR_HKS, i); }
+  __device__ __forceinline__ float inv_ths_sum(int i) const { return get(FR_INV_THS_SUM, i); }
+  __device__ __forceinline__ float rootr(int i) const { return get(FR_ROOTR, i); }
+  __device__ __forceinline__ float fmax() const { return base[(FR_NROWS * NL + 0) * STRIDE]; }
+  __device__ __forceinline__ float hksmin3() const { return base[(FR_NROWS * NL + 1) * STRIDE]; }
+
+  /* fill from the cell's parameters (once per launch) */
+  __device__ __forceinline__ void init(const Geo& g, const Params& p, const float (&rootr)[NL]) const {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
+      const float psi = p.psi_s[i], ths = p.theta_s[i], b = p.bsw[i];
+      const float e1 = 1.0f - 1.0f / b;
+      set(FR_PSI, i, psi);
+      set(FR_INV_NPSI, i, 1.0f / (-psi));
+      set(FR_E1, i, e1);
+      set(FR_COEF3, i, psi * ths / e1 / (g.zi[i + 1] - g.zi[i]));
+      set(FR_INV_THS, i, 1.0f / ths);
+      set(FR_THS, i, ths);
+      set(FR_BSW, i, b);
+      set(FR_HKS, i, p.hksat[i]);
+      set(FR_INV_THS_SUM, i, 1.0f / (ths + p.theta_s[ip]));
+      set(FR_ROOTR, i, rootr[i]);
+    }
+    base[(FR_NROWS * NL + 0) * STRIDE] = p.fmax;
+    base[(FR_NROWS * NL + 1) * STRIDE] = fminf(fminf(p.hksat[0], p.hksat[1]), p.hksat[2]);
+  }
+};
+
+struct FastState {
+  float h2o[NL], smp[NL];
+  float zwt, wa, rnf_sum;
+};
+
+/* per-day constants of the fast path: Day plus the reciprocals the sub-step multiplies by */
+struct DayFast {
+  float forc_rain, rain_dt;
+  float desatdT, gamma, dg, VDD, A;
+  float rsc_num, rsc_den0 /* 2*LAI*p28 */, rsc_floor;
+  float pmc_num, pms_num, inv_raa_rac, inv_raa_ras, inv_rac, inv_ras;
+  float Ra, dg_ras, dg_rac;
+  float raa_inv_rhocp, rhocp, lec_a, les_a, k_lamb /* 1e3/(rhow*lamb) */;
+  float litter10, litter1000;
+  bool canopy_on;
+};
+
+__device__ __forceinline__ void day_setup_fast(const Geo& g, const Forcing& f, float lai,
+                                                float lai_litter, DayFast& o, float& tas) {
+  Day d;
+  day_setup<MathFast>(g, f, lai, lai_litter, d);
+  tas = d.tas;
+  o.forc_rain = d.forc_rain;
+  o.rain_dt = d.rain_dt;
+  o.desatdT = d.desatdT;
+  o.gamma = d.gamma;
+  o.dg = d.dg;
+  o.VDD = d.VDD;
+  o.A = d.A;
+  o.rsc_num = d.rsc_num;
+  o.rsc_den0 = d.lai2 * d.p28;
+  o.rsc_floor = d.rsc_floor;
+  o.pmc_num = d.pmc_num;
+  o.pms_num = d.pms_num;
+  o.inv_raa_rac = MathFast::rcp(d.raa_rac);
+  o.inv_raa_ras = MathFast::rcp(d.raa_ras);
+  o.inv_rac = MathFast::rcp(d.rac);
+  o.inv_ras = MathFast::rcp(d.ras);
+  o.Ra = d.Ra;
+  o.dg_ras = d.dg_ras;
+  o.dg_rac = d.dg_rac;
+  o.rhocp = d.rhocp;
+  o.raa_inv_rhocp = d.raa * MathFast::rcp(d.rhocp);
+  o.lec_a = d.lec_a;
+  o.les_a = d.les_a;
+  o.k_lamb = 1.0E3f * MathFast::rcp(d.rhow_lamb);
+  o.litter10 = d.litter10;
+  o.litter1000 = d.litter1000;
+  o.canopy_on = d.canopy_on;
+}
+
+__device__ __forceinline__ float fast_pow(float a, float b) { return MathFast::ex2(b * MathFast::lg2(a)); }
+
+/* specific yield of layer I (0-based i) at water-table depth zwtmm, :963-965 */
+template <class C>
+__device__ __forceinline__ float fast_specific_yield(const C& c, int i, float zwtmm) {
+  const float s_y = c.ths(i) * (1.0f - fast_pow(fmaf(zwtmm, c.inv_npsi(i), 1.0f), -MathFast::rcp(c.bsw(i))));
+  return fmaxf(s_y, 0.02f);
+}
+
+template <class C>
+__device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c, const DayFast& d,
+                                                        FastState& s, StepOut& o) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  uint32_t fault = 0;
+  const float dt = g.dt, rdt = g.rdt;
+  float theta[NL];
+
+  /* :141-151 */
+  float w0 = d.rain_dt + s.wa;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    w0 += s.h2o[i];
+    theta[i] = s.h2o[i] * g.rdzw[i + 1];
+  }
+
+  /* SurfaceRunoff :182-212 */
+  const float fsat = c.fmax() * MathFast::ex2((-0.5f * kFff * kLog2e) * s.zwt);
+  float qflx_surf = fsat * d.forc_rain;
+
+  /* beta from the previous sub-step's smp :269-276: 1 - x/(-150000) == 1 + x/150000 */
+  float beta = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const float b = __saturatef(fmaf(s.smp[i] - g.zc[i + 1], 1.0f / 150000.0f, 1.0f));
+    beta = fmaf(c.rootr(i), b, beta);
+  }
+
+  /* rsc :283-295, rss :325-331 */
+  float rsc = (d.canopy_on && beta > 0.0f) ? d.rsc_num * MathFast::rcp(d.rsc_den0 * beta) : 1.0E6f;
+  rsc = fmaxf(rsc, d.rsc_floor);
+  const float rss = (theta[0] <= 0.15f)
+                        ? d.litter10 * MathFast::ex2((35.63f * kLog2e) * (0.15f - theta[0]))
+                        : fmaf(d.litter1000, 1.0f - theta[0] * c.inv_ths(0), 10.0f);
+
+  /* two-source Penman-Monteith :344-389 */
+  const float PMc = d.pmc_num * MathFast::rcp(fmaf(d.gamma, fmaf(rsc, d.inv_raa_rac, 1.0f), d.desatdT));
+  const float PMs = d.pms_num * MathFast::rcp(fmaf(d.gamma, fmaf(rss, d.inv_raa_ras, 1.0f), d.desatdT));
+  const float Rs = fmaf(d.gamma, rss, d.dg_ras);
+  const float Rc = fmaf(d.gamma, rsc, d.dg_rac);
+  /* Cc = 1/(1+Rc*Ra/(Rs*(Rc+Ra))) and Cs = 1/(1+Rs*Ra/(Rc*(Rs+Ra))) over the common
+   * denominator Rs*Rc + Rs*Ra + Rc*Ra */
+  const float RsRc = Rs * Rc, RsRa = Rs * d.Ra, RcRa = Rc * d.Ra;
+  const float invD = MathFast::rcp(RsRc + RsRa + RcRa);
+  const float LE = ((RsRc + RsRa) * PMc + (RsRc + RcRa) * PMs) * invD;
+  const float VDD0 = fmaf(d.A - d.dg * LE, d.raa_inv_rhocp, d.VDD);
+  const float rv = d.rhocp * VDD0;
+  const float LEc = fmaf(rv, d.inv_rac, d.lec_a) * MathFast::rcp(fmaf(d.gamma, fmaf(rsc, d.inv_rac, 1.0f), d.desatdT));
+  const float LEs = fmaf(rv, d.inv_ras, d.les_a) * MathFast::rcp(fmaf(d.gamma, fmaf(rss, d.inv_ras, 1.0f), d.desatdT));
+  const float qflx_tran_veg_col = LEc * d.k_lamb;
+  float qflx_evap_grnd = LEs * d.k_lamb;
+
+  /* evaporation limit :396-400 */
+  const float evap_max1 = fmaxf(0.0f, g.dz[1] * (theta[0] - kWatmin) * rdt - qflx_tran_veg_col * c.rootr(0));
+  qflx_evap_grnd = fminf(evap_max1, qflx_evap_grnd);
+
+  /* Infiltration :426-478 */
+  const float qflx_in_soil = (d.forc_rain - qflx_surf) - qflx_evap_grnd;
+  const float qinmax = (1.0f - fsat) * c.hksmin3();
+  const float qflx_infl_excess = fmaxf(0.0f, qflx_in_soil - qinmax);
+  const float qflx_infl = qflx_in_soil - qflx_infl_excess;
+  qflx_surf += qflx_infl_excess;
+
+  /* SoilWater :492-508 */
+  float zwtmm = 1000.0f * s.zwt;
+  int jwt = find_jwt(g, s.zwt);
+  const bool deep = (jwt == NL);
+
+  /* equilibrium profile :517-590 */
+  float zq[NL + 1];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const float zlo = g.zi[i], zhi = g.zi[i + 1];
+    const float ths = c.ths(i), psi = c.psi(i);
+    const float npz = zwtmm - psi; /* (-psi) + zwtmm */
+    float vol = ths;
+    if (zwtmm > zlo) {
+      const float inv_npsi = c.inv_npsi(i), e1 = c.e1(i);
+      const float temp0 = fast_pow((npz - zlo) * inv_npsi, e1);
+      if (zwtmm < zhi) { /* water table inside the layer :525-542 */
+        /* voleq1*(zwtmm-zlo) == (psi*ths/e1)*(1-temp0): the division by (zwtmm-zlo) cancels */
+        const float coefA = c.coef3(i) * (zhi - zlo);
+        vol = fmaf(coefA, 1.0f - temp0, ths * (zhi - zwtmm)) * g.rdzl[i + 1];
+        vol = fmaxf(fminf(ths, vol), 0.0f);
+      } else { /* water table below the layer :548-558 */
+        const float tempi = fast_pow((npz - zhi) * inv_npsi, e1);
+        vol = c.coef3(i) * (tempi - temp0);
+        vol = fminf(ths, fmaxf(vol, 0.0f));
+      }
+    }
+    zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+  }
+  zq[NL] = 0.0f;
+  if (deep) { /* :576-590 */
+    const int i = NL - 1;
+    const float ths = c.ths(i), psi = c.psi(i), zhi = g.zi[NL];
+    const float temp0 = fast_pow(((zwtmm - psi) - zhi) * c.inv_npsi(i), c.e1(i));
+    const float coefA = c.coef3(i) * (zhi - g.zi[NL - 1]);
+    float vol = coefA * MathFast::rcp(zwtmm - zhi) * (1.0f - temp0);
+    vol = fminf(ths, fmaxf(vol, 0.0f));
+    zq[NL] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+  }
+
+  /* hk, dhkdw, smp, dsmpdw :598-639 */
+  float hk[NL], dhkdw[NL], dsmpdw[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
+    const float b = c.bsw(i), its = c.inv_ths_sum(i);
+    const float s1 = fminf(1.0f, (theta[i] + theta[ip]) * its);
+    const float s2 = c.hks(i) * fast_pow(s1, fmaf(2.0f, b, 2.0f));
+    hk[i] = s1 * s2;
+    dhkdw[i] = fmaf(2.0f, b, 3.0f) * s2 * its;
+    const float inv_ths = c.inv_ths(i);
+    const float s_node = fminf(1.0f, fmaxf(theta[i] * inv_ths, 0.01f));
+    const float sm = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
+    s.smp[i] = sm;
+    dsmpdw[i] = (-b * inv_ths) * sm * MathFast::rcp(s_node);
+  }
+
+  /* aquifer node :645-650 and its interface :737-753; inert when the table is in the column */
+  const float dz9 = deep ? (zwtmm - g.zc[NL]) : g.dz[NL];
+  float q[NL], qa[NL], qb[NL]; /* per interface i (below layer i): flux and its two derivatives */
+#pragma unroll
+  for (int i = 0; i < NL - 1; ++i) {
+    const float rden = g.rden[i + 1];
+    const float num = (s.smp[i + 1] - s.smp[i]) - (zq[i + 1] - zq[i]);
+    const float nd = num * dhkdw[i];
+    q[i] = -hk[i] * num * rden;                 /* qout(I) == qin(I+1) */
+    qa[i] = fmaf(hk[i], dsmpdw[i], -nd) * rden; /* dqodw1(I) == dqidw0(I+1) */
+    qb[i] = -fmaf(hk[i], dsmpdw[i + 1], nd) * rden; /* dqodw2(I) == dqidw1(I+1) */
+  }
+  {
+    const int i = NL - 1;
+    q[i] = qa[i] = qb[i] = 0.0f;
+    if (deep) {
+      const float b = c.bsw(i), inv_ths = c.inv_ths(i);
+      const float s_node = fminf(1.0f, fmaxf(0.5f * fmaf(theta[i], inv_ths, 1.0f), 0.01f));
+      const float smp1 = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
+      const float dsmpdw1 = (-b * inv_ths) * smp1 * MathFast::rcp(s_node);
+      const float zc9 = 0.5f * (zwtmm + g.zc[NL]);
+      const float rden = MathFast::rcp(zc9 - g.zc[NL]);
+      const float num = (smp1 - s.smp[i]) - (zq[NL] - zq[i]);
+      const float nd = num * dhkdw[i];
+      q[i] = -hk[i] * num * rden;
+      qa[i] = fmaf(hk[i], dsmpdw[i], -nd) * rden;
+      qb[i] = -fmaf(hk[i], dsmpdw1, nd) * rden;
+    }
+  }
+
+  /* tridiagonal rows :661-799 fused with the Thomas forward sweep :806-827 */
+  float dwat2[NL + 1], gam[NL + 1];
+  float bet, rbet;
+  {
+    const float rmx = (qflx_infl - q[0]) - qflx_tran_veg_col * c.rootr(0);
+    bet = g.dzdt[1] + qa[0];
+    if (bet == 0.0f) fault |= FAULT_PIVOT1;
+    rbet = MathFast::rcp(bet);
+    dwat2[0] = rmx * rbet;
+  }
+#pragma unroll
+  for (int i = 1; i < NL; ++i) {
+    const float rmx = (q[i - 1] - q[i]) - qflx_tran_veg_col * c.rootr(i);
+    const float amx = -qa[i - 1];
+    const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
+    gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
+    bet = fmaf(-amx, gam[i], bmx);
+    if (bet == 0.0f) fault |= FAULT_PIVOT2;
+    rbet = MathFast::rcp(bet);
+    dwat2[i] = fmaf(-amx, dwat2[i - 1], rmx) * rbet;
+  }
+  { /* aquifer row */
+    const float rmx = q[NL - 1];
+    const float amx = -qa[NL - 1];
+    const float bmx = dz9 * rdt - qb[NL - 1];
+    gam[NL] = qb[NL - 1] * rbet;
+    bet = fmaf(-amx, gam[NL], bmx);
+    if (bet == 0.0f) fault |= FAULT_PIVOT2;
+    dwat2[NL] = fmaf(-amx, dwat2[NL - 1], rmx) * MathFast::rcp(bet);
+  }
+#pragma unroll
+  for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
+
+  /* :845-850 */
+#pragma unroll
+  for (int i = 0; i < NL; ++i) s.h2o[i] = fmaf(dwat2[i], g.dz[i + 1], s.h2o[i]);
+
+  /* recharge :856-904 */
+  float qcharge;
+  if (!deep) {
+    const int jm = (jwt > 1 ? jwt : 1) - 1;
+    const float th_j = pick<NL>(theta, jwt);
+    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
+    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
+    const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
+    float zq_j = zq[0];
+#pragma unroll
+    for (int k = 1; k < NL; ++k)
+      if (jm == k) zq_j = zq[k];
+    const float wh = smp1 - zq_j;
+    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    qcharge = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
+    qcharge = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge));
+  } else {
+    qcharge = dwat2[NL] * dz9 * rdt;
+  }
+
+  /* Drainage :923-1009 */
+  jwt = find_jwt(g, s.zwt);
+  float rous = fast_specific_yield(c, NL - 1, zwtmm);
+  if (jwt == NL) {
+    s.wa = fmaf(qcharge, dt, s.wa);
+    s.zwt -= qcharge * dt * 0.001f * MathFast::rcp(rous);
+  } else { /* zwtmm stays the stale value of :492 inside the loops */
+    float qcharge_tot = qcharge * dt;
+    if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
+      for (int I = jwt + 1; I >= 1; --I) {
+        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
+        s.zwt -= ql * MathFast::rcp(s_y) * 0.001f; /* s_y >= 0.02 > 0 */
+        qcharge_tot -= ql;
+        if (qcharge_tot <= 0.0f) break;
+      }
+    } else { /* deepening, layers jwt+1 .. 8 */
+      for (int I = jwt + 1; I <= NL; ++I) {
+        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
+        qcharge_tot -= ql;
+        if (qcharge_tot >= 0.0f) {
+          s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
+          break;
+        }
+        s.zwt = g.zim[I];
+      }
+      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * MathFast::rcp(rous);
+    }
+    jwt = find_jwt(g, s.zwt);
+  }
+
+  zwtmm = 1000.0f * s.zwt; /* :1015 */
+
+  /* baseflow :1024-1118 */
+  float rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
+  rous = fast_specific_yield(c, NL - 1, zwtmm);
+  if (jwt == NL) { /* jwt is not recomputed on this path */
+    s.wa = fmaf(-rsub_top, dt, s.wa);
+    s.zwt += rsub_top * dt * 0.001f * MathFast::rcp(rous);
+    s.h2o[NL - 1] += fmaxf(0.0f, s.wa - 5000.0f);
+    s.wa = fminf(s.wa, 5000.0f);
+  } else {
+    float rsub_top_tot = -rsub_top * dt;
+    if (rsub_top_tot > 0.0f) {
+      fault |= FAULT_RSUB;
+    } else {
+      for (int I = jwt + 1; I <= NL; ++I) {
+        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+        const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+          if (k == I - 1) s.h2o[k] += rl;
+        rsub_top_tot -= rl;
+        if (rsub_top_tot >= 0.0f) {
+          s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
+          break;
+        }
+        s.zwt = g.zim[I];
+      }
+      s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* residual, unconditional :1100-1101 */
+      s.wa += rsub_top_tot;
+    }
+    jwt = find_jwt(g, s.zwt);
+  }
+
+  s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
+
+  /* excess cascade :1131-1152 */
+#pragma unroll
+  for (int i = NL - 1; i >= 1; --i) {
+    const float cap = fmaxf(0.01f, c.ths(i)) * g.dz[i + 1];
+    const float xsi = fmaxf(s.h2o[i] - cap, 0.0f);
+    s.h2o[i] = fminf(cap, s.h2o[i]);
+    s.h2o[i - 1] += xsi;
+  }
+  const float cap1 = fmaxf(0.0f, c.ths(0) * g.dz[1]);
+  const float xs1 = fmaxf(fmaxf(s.h2o[0], 0.0f) - cap1, 0.0f);
+  s.h2o[0] = fminf(cap1, s.h2o[0]);
+  const float qflx_rsub_sat = xs1 * rdt;
+
+  /* dryness repair :1161-1205 */
+  float xs;
+#pragma unroll
+  for (int i = 0; i < NL - 1; ++i) {
+    xs = fmaxf(kWatmin - s.h2o[i], 0.0f); /* > 0 exactly when h2o < watmin */
+    if (xs > 0.0f && i + 1 == jwt) s.zwt += xs * MathFast::rcp(fmaxf(0.01f, c.ths(i))) * 0.001f;
+    s.h2o[i] += xs;
+    s.h2o[i + 1] -= xs;
+  }
+  xs = 0.0f;
+  if (s.h2o[NL - 1] < kWatmin) { /* rare: search upward for water :1181-1198 */
+    xs = kWatmin - s.h2o[NL - 1];
+    bool done = false;
+#pragma unroll
+    for (int j = NL - 2; j >= 0; --j) {
+      if (!done) {
+        const float avail = fmaxf(s.h2o[j] - kWatmin - xs, 0.0f);
+        const float take = (avail >= xs) ? xs : avail;
+        done = (avail >= xs);
+        s.h2o[NL - 1] += take;
+        s.h2o[j] -= take;
+        xs = done ? 0.0f : xs - take;
+      }
+    }
+  }
+  s.h2o[NL - 1] += xs;  /* :1205 */
+  rsub_top -= xs * rdt; /* :1211 */
+
+  /* balance :1221-1244 */
+  float w1 = fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) w1 += s.h2o[i];
+  const float imb = w1 - w0;
+  if (!(fabsf(imb) <= 0.1f)) fault |= FAULT_IMBAL;
+
+  /* :1282-1283 */
+  const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
+  s.rnf_sum = (s.rnf_sum + r1) + r2;
+
+  o.qflx_tran_veg_col = qflx_tran_veg_col;
+  o.qflx_evap_grnd = qflx_evap_grnd;
+  o.rnf_inc = r1 + r2;
+  o.imbalance = imb;
+  o.jwt = jwt;
+  return fault;
+}
+
+} /* namespace h9 */
+#endif
