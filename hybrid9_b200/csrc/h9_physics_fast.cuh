@@ -205,28 +205,23 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   int jwt = find_jwt(g, s.zwt);
   const bool deep = (jwt == NL);
 
-  /* equilibrium profile :517-590 */
+  /* equilibrium profile :517-590, branch-free.  With B0 = (-psi+zwtmm-zi(I-1))/(-psi) and
+   * BI = (-psi+zwtmm-zi(I))/(-psi), the three cases of the reference are one formula:
+   *   vol = [ A*(max(BI,1)**e1 - max(B0,1)**e1) + ths*max(zi(I)-zwtmm,0) ] / dz,  A = psi*ths/e1
+   * below the layer both bases are >= 1 and the last term vanishes (:548-558); inside it
+   * BI < 1 so the first power is tempi = 1 (:532-540); above it both powers are 1 and
+   * (zi(I)-zwtmm)/dz >= 1 so the clamp to theta_s returns theta_s (:523). */
   float zq[NL + 1];
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const float zlo = g.zi[i], zhi = g.zi[i + 1];
-    const float ths = c.ths(i), psi = c.psi(i);
+    const float ths = c.ths(i), psi = c.psi(i), inv_npsi = c.inv_npsi(i), e1 = c.e1(i);
     const float npz = zwtmm - psi; /* (-psi) + zwtmm */
-    float vol = ths;
-    if (zwtmm > zlo) {
-      const float inv_npsi = c.inv_npsi(i), e1 = c.e1(i);
-      const float temp0 = fast_pow((npz - zlo) * inv_npsi, e1);
-      if (zwtmm < zhi) { /* water table inside the layer :525-542 */
-        /* voleq1*(zwtmm-zlo) == (psi*ths/e1)*(1-temp0): the division by (zwtmm-zlo) cancels */
-        const float coefA = c.coef3(i) * (zhi - zlo);
-        vol = fmaf(coefA, 1.0f - temp0, ths * (zhi - zwtmm)) * g.rdzl[i + 1];
-        vol = fmaxf(fminf(ths, vol), 0.0f);
-      } else { /* water table below the layer :548-558 */
-        const float tempi = fast_pow((npz - zhi) * inv_npsi, e1);
-        vol = c.coef3(i) * (tempi - temp0);
-        vol = fminf(ths, fmaxf(vol, 0.0f));
-      }
-    }
+    const float t0 = fast_pow(fmaxf((npz - zlo) * inv_npsi, 1.0f), e1);
+    const float ti = fast_pow(fmaxf((npz - zhi) * inv_npsi, 1.0f), e1);
+    const float coefA = c.coef3(i) * (zhi - zlo); /* psi*ths/e1 */
+    float vol = fmaf(coefA, ti - t0, ths * fmaxf(zhi - zwtmm, 0.0f)) * g.rdzl[i + 1];
+    vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
   }
   zq[NL] = 0.0f;
@@ -289,12 +284,13 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   /* tridiagonal rows :661-799 fused with the Thomas forward sweep :806-827 */
   float dwat2[NL + 1], gam[NL + 1];
-  float bet, rbet;
+  float bet, rbet, minpiv;
   {
     const float rmx = (qflx_infl - q[0]) - qflx_tran_veg_col * c.rootr(0);
     bet = g.dzdt[1] + qa[0];
     if (bet == 0.0f) fault |= FAULT_PIVOT1;
     rbet = MathFast::rcp(bet);
+    minpiv = 3.0e38f;
     dwat2[0] = rmx * rbet;
   }
 #pragma unroll
@@ -304,7 +300,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
     gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
     bet = fmaf(-amx, gam[i], bmx);
-    if (bet == 0.0f) fault |= FAULT_PIVOT2;
+    minpiv = fminf(minpiv, fabsf(bet));
     rbet = MathFast::rcp(bet);
     dwat2[i] = fmaf(-amx, dwat2[i - 1], rmx) * rbet;
   }
@@ -314,9 +310,10 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     const float bmx = dz9 * rdt - qb[NL - 1];
     gam[NL] = qb[NL - 1] * rbet;
     bet = fmaf(-amx, gam[NL], bmx);
-    if (bet == 0.0f) fault |= FAULT_PIVOT2;
+    minpiv = fminf(minpiv, fabsf(bet));
     dwat2[NL] = fmaf(-amx, dwat2[NL - 1], rmx) * MathFast::rcp(bet);
   }
+  if (minpiv == 0.0f) fault |= FAULT_PIVOT2; /* BET == 0 in some row :818 */
 #pragma unroll
   for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
 
@@ -344,8 +341,8 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     qcharge = dwat2[NL] * dz9 * rdt;
   }
 
-  /* Drainage :923-1009 */
-  jwt = find_jwt(g, s.zwt);
+  /* Drainage :923-1009.  The jwt of :923-931 equals the one of :499-508: zwt has not
+   * changed in between */
   float rous = fast_specific_yield(c, NL - 1, zwtmm);
   if (jwt == NL) {
     s.wa = fmaf(qcharge, dt, s.wa);
@@ -412,41 +409,52 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
 
-  /* excess cascade :1131-1152 */
+  /* excess cascade :1131-1152: a no-op unless some layer is above its capacity */
+  float over = s.h2o[0] - fmaxf(0.0f, c.ths(0) * g.dz[1]);
 #pragma unroll
-  for (int i = NL - 1; i >= 1; --i) {
-    const float cap = fmaxf(0.01f, c.ths(i)) * g.dz[i + 1];
-    const float xsi = fmaxf(s.h2o[i] - cap, 0.0f);
-    s.h2o[i] = fminf(cap, s.h2o[i]);
-    s.h2o[i - 1] += xsi;
+  for (int i = 1; i < NL; ++i) over = fmaxf(over, s.h2o[i] - fmaxf(0.01f, c.ths(i)) * g.dz[i + 1]);
+  float qflx_rsub_sat = 0.0f;
+  if (over > 0.0f) {
+#pragma unroll
+    for (int i = NL - 1; i >= 1; --i) {
+      const float cap = fmaxf(0.01f, c.ths(i)) * g.dz[i + 1];
+      const float xsi = fmaxf(s.h2o[i] - cap, 0.0f);
+      s.h2o[i] = fminf(cap, s.h2o[i]);
+      s.h2o[i - 1] += xsi;
+    }
+    const float cap1 = fmaxf(0.0f, c.ths(0) * g.dz[1]);
+    const float xs1 = fmaxf(fmaxf(s.h2o[0], 0.0f) - cap1, 0.0f);
+    s.h2o[0] = fminf(cap1, s.h2o[0]);
+    qflx_rsub_sat = xs1 * rdt;
   }
-  const float cap1 = fmaxf(0.0f, c.ths(0) * g.dz[1]);
-  const float xs1 = fmaxf(fmaxf(s.h2o[0], 0.0f) - cap1, 0.0f);
-  s.h2o[0] = fminf(cap1, s.h2o[0]);
-  const float qflx_rsub_sat = xs1 * rdt;
 
-  /* dryness repair :1161-1205 */
-  float xs;
+  /* dryness repair :1161-1205: a no-op unless some layer is below watmin */
+  float lowest = s.h2o[0];
 #pragma unroll
-  for (int i = 0; i < NL - 1; ++i) {
-    xs = fmaxf(kWatmin - s.h2o[i], 0.0f); /* > 0 exactly when h2o < watmin */
-    if (xs > 0.0f && i + 1 == jwt) s.zwt += xs * MathFast::rcp(fmaxf(0.01f, c.ths(i))) * 0.001f;
-    s.h2o[i] += xs;
-    s.h2o[i + 1] -= xs;
-  }
-  xs = 0.0f;
-  if (s.h2o[NL - 1] < kWatmin) { /* rare: search upward for water :1181-1198 */
-    xs = kWatmin - s.h2o[NL - 1];
-    bool done = false;
+  for (int i = 1; i < NL; ++i) lowest = fminf(lowest, s.h2o[i]);
+  float xs = 0.0f;
+  if (lowest < kWatmin) {
 #pragma unroll
-    for (int j = NL - 2; j >= 0; --j) {
-      if (!done) {
-        const float avail = fmaxf(s.h2o[j] - kWatmin - xs, 0.0f);
-        const float take = (avail >= xs) ? xs : avail;
-        done = (avail >= xs);
-        s.h2o[NL - 1] += take;
-        s.h2o[j] -= take;
-        xs = done ? 0.0f : xs - take;
+    for (int i = 0; i < NL - 1; ++i) {
+      xs = fmaxf(kWatmin - s.h2o[i], 0.0f); /* > 0 exactly when h2o < watmin */
+      if (xs > 0.0f && i + 1 == jwt) s.zwt += xs * MathFast::rcp(fmaxf(0.01f, c.ths(i))) * 0.001f;
+      s.h2o[i] += xs;
+      s.h2o[i + 1] -= xs;
+    }
+    xs = 0.0f;
+    if (s.h2o[NL - 1] < kWatmin) { /* search upward for water :1181-1198 */
+      xs = kWatmin - s.h2o[NL - 1];
+      bool done = false;
+#pragma unroll
+      for (int j = NL - 2; j >= 0; --j) {
+        if (!done) {
+          const float avail = fmaxf(s.h2o[j] - kWatmin - xs, 0.0f);
+          const float take = (avail >= xs) ? xs : avail;
+          done = (avail >= xs);
+          s.h2o[NL - 1] += take;
+          s.h2o[j] -= take;
+          xs = done ? 0.0f : xs - take;
+        }
       }
     }
   }
