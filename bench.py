@@ -152,7 +152,7 @@ def cpu_baseline(world, forcing, nisurf, seconds, kind_note=""):
     import oracle_py
     from hybrid9_b200 import synth
     cores = os.cpu_count() or 1
-    ncell = int(min(world.land.sum(), 256 * cores))
+    ncell = int(min(world.land.sum(), 1024 * cores))
     days_avail = forcing["tas"].shape[0]
 
     def run(nd):
@@ -392,6 +392,12 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {ex}"}
 
+    # regime of the final state (outside the timed region): share of cells whose water table
+    # is inside the soil column (jwt < 8), which take the branchier Drainage path
+    st_end = h.get_state()
+    land_mask_ = world.land
+    shallow = float((st_end.zwt[land_mask_] <= synth.ZI_DRIVER[8] / 1000.0).mean()) if nc else 0.0
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size,
@@ -403,7 +409,8 @@ def main():
                                    f"{label} sharded in latitude bands: {sum(n_land_all)} land cells "
                                    f"x {nd} days x {nis} sub-steps per step",
                        "land_cells_per_gpu": n_land_all, "days_per_step": nd, "nisurf": nis,
-                       "math": args.math,
+                       "math": args.math, "simulated_years": year[0],
+                       "share_cells_water_table_in_soil_column_at_end": round(shallow, 4),
                        "l2": "forcing stream (689 MB/step at 0.5deg) exceeds L2; state is "
                              "register/L2 resident by design",
                        "parallelism": f"dp{world_size} latitude bands, no data-path collective"},

@@ -313,7 +313,7 @@ int h9_create(h9_ctx** out, int device_id) {
   const char* td = getenv("H9_TILE_DAYS");
   if (td && atoi(td) > 0) ctx->tile_days = atoi(td);
   const char* bl = getenv("H9_BLOCK");
-  if (bl && (atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
+  if (bl && (atoi(bl) == 2000 || atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
   *out = ctx;
   return H9_OK;
 }
@@ -372,7 +372,7 @@ int h9_set_math(h9_ctx* ctx, int mode) {
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block) {
   if (!ctx) return H9_ERR_ARG;
   if (tile_days > 0) ctx->tile_days = tile_days;
-  if (block % 1000 == 32 || block % 1000 == 64 || block % 1000 == 128) ctx->block = block;
+  if (block == 2000 || block % 1000 == 32 || block % 1000 == 64 || block % 1000 == 128) ctx->block = block;
   return H9_OK;
 }
 

@@ -19,10 +19,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
                  const int32_t* __restrict__ year_index, const float* __restrict__ forcing,
                  size_t day_stride, size_t plane_stride, int cur_year, int nt,
-                 unsigned long long step0) {
+                 unsigned long long step0, int cells_per_block) {
   extern __shared__ float smem[];
-  const int c = blockIdx.x * BLOCK + threadIdx.x;
-  if (c >= a.nc) return; /* no barriers below: every thread only touches its own column */
+  /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells */
+  const int c = blockIdx.x * cells_per_block + threadIdx.x;
+  if (threadIdx.x >= cells_per_block || c >= a.nc) return; /* no barriers below */
   const CellTable<BLOCK> tbl{smem + threadIdx.x};
 
   FastState s;
@@ -194,7 +195,24 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
                      int block) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a.nc <= 0 || ndays <= 0) return 0;
-  /* block: threads per block (32/64/128), +1000 for the <=128-register variant (default) */
+  /* block: threads per block (32/64/128), +1000 for the <=128-register variant;
+   * 2000 = balanced: one wide block per SM and wave, every SM gets the same cell count */
+  if (block >= 2000) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int waves = (a.nc + nsm * 512 - 1) / (nsm * 512);
+    const int nblk = nsm * waves;
+    const int cpb = (a.nc + nblk - 1) / nblk;
+    const int threads = (cpb + 31) / 32 * 32;
+    const size_t shm = (size_t)kFastFloatsPerCell * 512 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(days_kernel_fast<512, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    if (e != cudaSuccess) return (int)e;
+    days_kernel_fast<512, 1><<<(a.nc + cpb - 1) / cpb, threads, shm, st>>>(
+        a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0, cpb);
+    return (int)cudaGetLastError();
+  }
   const bool capped = block >= 1000;
   const int bs = block % 1000;
 #define H9_LAUNCH(BS, MINB)                                                                    \
@@ -204,7 +222,7 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
     if (e != cudaSuccess) return (int)e;                                                       \
     days_kernel_fast<BS, MINB><<<(a.nc + BS - 1) / BS, BS, shm, st>>>(                         \
-        a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0);  \
+        a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0, BS);  \
   } while (0)
   if (bs == 32) {
     if (capped) H9_LAUNCH(32, 16); else H9_LAUNCH(32, 1);

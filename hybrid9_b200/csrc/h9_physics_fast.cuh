@@ -212,25 +212,38 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
    * BI < 1 so the first power is tempi = 1 (:532-540); above it both powers are 1 and
    * (zi(I)-zwtmm)/dz >= 1 so the clamp to theta_s returns theta_s (:523). */
   float zq[NL + 1];
+  /* (a variant specialised for the all-layers-below case was slower: warps that mix deep and
+   * shallow cells then execute both loops) */
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const float zlo = g.zi[i], zhi = g.zi[i + 1];
     const float ths = c.ths(i), psi = c.psi(i), inv_npsi = c.inv_npsi(i), e1 = c.e1(i);
-    const float npz = zwtmm - psi; /* (-psi) + zwtmm */
-    const float t0 = fast_pow(fmaxf((npz - zlo) * inv_npsi, 1.0f), e1);
-    const float ti = fast_pow(fmaxf((npz - zhi) * inv_npsi, 1.0f), e1);
+    /* (-psi+zwtmm-z)/(-psi) evaluated as 1 + (zwtmm-z)/(-psi): same value, no cancellation */
+    const float t0 = fast_pow(fmaxf(fmaf(zwtmm - zlo, inv_npsi, 1.0f), 1.0f), e1);
+    const float ti = fast_pow(fmaxf(fmaf(zwtmm - zhi, inv_npsi, 1.0f), 1.0f), e1);
     const float coefA = c.coef3(i) * (zhi - zlo); /* psi*ths/e1 */
     float vol = fmaf(coefA, ti - t0, ths * fmaxf(zhi - zwtmm, 0.0f)) * g.rdzl[i + 1];
     vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
   }
   zq[NL] = 0.0f;
-  if (deep) { /* :576-590 */
+  if (deep) { /* :576-590: vol_eq(9) = A/(zwtmm-zi(8)) * (1 - (1+u)**e1), u = (zwtmm-zi(8))/(-psi) */
     const int i = NL - 1;
-    const float ths = c.ths(i), psi = c.psi(i), zhi = g.zi[NL];
-    const float temp0 = fast_pow(((zwtmm - psi) - zhi) * c.inv_npsi(i), c.e1(i));
-    const float coefA = c.coef3(i) * (zhi - g.zi[NL - 1]);
-    float vol = coefA * MathFast::rcp(zwtmm - zhi) * (1.0f - temp0);
+    const float ths = c.ths(i), psi = c.psi(i), e1 = c.e1(i), inv_npsi = c.inv_npsi(i);
+    const float u = (zwtmm - g.zi[NL]) * inv_npsi;
+    /* r = ((1+u)**e1 - 1)/u.  The direct form loses every digit as the water table nears the
+     * column base (u -> 0, where the reference's own float evaluation is noise); the
+     * binomial series keeps r accurate there. */
+    float r;
+    if (u < 0.03f) {
+      const float a2 = 0.5f * (e1 - 1.0f), a3 = (1.0f / 3.0f) * (e1 - 2.0f), a4 = 0.25f * (e1 - 3.0f);
+      r = e1 * fmaf(u * a2, fmaf(u * a3, fmaf(u, a4, 1.0f), 1.0f), 1.0f);
+    } else {
+      r = (fast_pow(1.0f + u, e1) - 1.0f) * MathFast::rcp(u);
+    }
+    /* A/(zwtmm-zi(8)) * (1-temp0) = -A * inv_npsi * r */
+    const float coefA = c.coef3(i) * (g.zi[NL] - g.zi[NL - 1]);
+    float vol = -coefA * inv_npsi * r;
     vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[NL] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
   }

@@ -68,3 +68,27 @@ def test_latitude_band_shards_reproduce_the_whole(big, nranks):
         for n in ("h2osoi_liq", "zwt", "wa", "lai", "plant_mass", "smp", "rootr_col"):
             assert np.array_equal(getattr(st, n)[sub.land], getattr(whole, n)[ys][sub.land]), (r, n)
         assert np.array_equal(a["rnf"], ann["rnf"][ys], equal_nan=True)
+
+
+def test_multi_decade_spin_up_runs_clean():
+    """BASELINE.json config 4 in miniature: 30 simulated years from the INIT state on the
+    full 0.5 deg land mask, fast mode, one fused launch per year.  No cell may trip one of
+    the reference's STOP conditions, and the water table must stay in its legal range.
+    (Cells whose water table hovers at the base of the soil column exercise the
+    ill-conditioned aquifer-layer formula HYDROLOGY.f90:576-590.)"""
+    w = synth.make_world()
+    nd = 365
+    f = synth.make_forcing(w, nd, seed=9)
+    h = make_gpu(w, mode=MATH_FAST, nyr=2)
+    h.set_state(init_state(w.soil_tex, w.theta_s, synth.ZI_DRIVER), with_smp=False)
+    p, ds, ps = h.pack_forcing(f, nd)
+    for yr in range(30):
+        rc = h.run_days_device(np.full(nd, yr % 2 + 1, np.int32), p, ds, ps)
+        assert rc == 0, (yr + 1, h.get_fault())
+    st = h.get_state()
+    land = w.land
+    assert (st.zwt[land] >= 0).all() and (st.zwt[land] <= 80).all()
+    assert np.isfinite(st.h2osoi_liq[land]).all() and (st.plant_mass[land] > 0).all()
+    shallow = (st.zwt[land] <= 2.296).mean()
+    assert 0.0 < shallow < 1.0   # both Drainage regimes are populated after the spin-up
+    h.close()
