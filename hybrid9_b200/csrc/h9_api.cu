@@ -35,6 +35,11 @@ struct h9_ctx {
   size_t ngrid = 0;
   int math_mode = H9_MATH_FAST;
   int tile_days = 8, block = 1064; /* 64 threads/block, 128-register variant */
+  /* h9_run_days ingest (env H9_INGEST): 3 hostread (default; page-locked arrays are read in
+   * place by the stepping kernel, pageable ones fall back to gather), 0 gather, 1 pack,
+   * 2 zerocopy pack */
+  int ingest = 3;
+  bool zero_copy = false;
   Geo geo;
   std::vector<int32_t> cell_xy;
   DevArrays dev;
@@ -148,16 +153,23 @@ cudaEvent_t get_event(h9_ctx* ctx) {
   return e;
 }
 
-int launch_days(h9_ctx* ctx, int ndays, const int32_t* d_yi, const float* d_forcing,
-                size_t day_stride, size_t plane_stride) {
+ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stride) {
+  ForcingView fv;
+  for (int p = 0; p < kForcingPlanes; ++p) fv.plane[p] = base + p * plane_stride;
+  fv.day_stride = day_stride;
+  return fv;
+}
+
+int launch_days(h9_ctx* ctx, int ndays, const int32_t* d_yi, const ForcingView& fv,
+                const int32_t* d_cell_index = nullptr) {
   cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
   CK(cudaEventRecord(e0, ctx->stream));
   if (ctx->math_mode == H9_MATH_EXACT) {
-    CKL(launch_days_exact(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, d_forcing, day_stride,
-                          plane_stride, ctx->cur_year, ctx->nt, ctx->step_counter, ctx->block));
+    CKL(launch_days_exact(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, fv, ctx->cur_year, ctx->nt,
+                          ctx->step_counter, ctx->block, d_cell_index));
   } else {
-    CKL(launch_days_fast(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, d_forcing, day_stride,
-                         plane_stride, ctx->cur_year, ctx->nt, ctx->step_counter, ctx->block));
+    CKL(launch_days_fast(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, fv, ctx->cur_year, ctx->nt,
+                         ctx->step_counter, ctx->block, d_cell_index));
   }
   CK(cudaEventRecord(e1, ctx->stream));
   ctx->timing.emplace_back(e0, e1);
@@ -222,25 +234,38 @@ int ensure_stage(h9_ctx* ctx, bool need_host_stage) {
   return 0;
 }
 
-/* copy days [d0,d0+nd) of the seven (lon_c,lat_c,ndays) host arrays into stage
- * buffer b as [7][nd][ngrid] and pack them into `d_out` ([nd][7][ncs]) on the
- * copy stream */
+/* days [d0,d0+nd) of the seven (lon_c,lat_c,ndays) host arrays -> `d_out` ([nd][7][ncs]) on
+ * the copy stream.  Page-locked arrays are gathered in place by the pack kernel (zero-copy:
+ * only land cells cross PCIe); pageable ones are bounced through the pinned ring and copied
+ * to stage buffer b first. */
 int stage_and_pack(h9_ctx* ctx, int b, int d0, int nd, const float* const src[7], bool pinned,
                    float* d_out) {
   const size_t plane = (size_t)nd * ctx->ngrid;
-  for (int p = 0; p < kForcingPlanes; ++p) {
-    const float* hp = src[p] + (size_t)d0 * ctx->ngrid;
-    if (!pinned) { /* pageable caller memory: bounce through our pinned ring */
-      memcpy(ctx->h_stage[b] + p * plane, hp, plane * sizeof(float));
-      hp = ctx->h_stage[b] + p * plane;
+  const float* planes[kForcingPlanes];
+  if (pinned && ctx->zero_copy) {
+    for (int p = 0; p < kForcingPlanes; ++p) {
+      void* dp = nullptr;
+      CK(cudaHostGetDevicePointer(&dp, (void*)(src[p] + (size_t)d0 * ctx->ngrid), 0));
+      planes[p] = (const float*)dp;
     }
-    CK(cudaMemcpyAsync(ctx->d_stage[b] + p * plane, hp, plane * sizeof(float),
-                       cudaMemcpyHostToDevice, ctx->copy_stream));
-    ctx->h2d += (int64_t)(plane * sizeof(float));
+    /* bytes that cross the bus: the land cells' values (32-byte sector granularity ignored) */
+    ctx->h2d += (int64_t)nd * kForcingPlanes * ctx->dev.nc * (int64_t)sizeof(float);
+  } else {
+    for (int p = 0; p < kForcingPlanes; ++p) {
+      const float* hp = src[p] + (size_t)d0 * ctx->ngrid;
+      if (!pinned) { /* pageable caller memory: bounce through our pinned ring */
+        memcpy(ctx->h_stage[b] + p * plane, hp, plane * sizeof(float));
+        hp = ctx->h_stage[b] + p * plane;
+      }
+      CK(cudaMemcpyAsync(ctx->d_stage[b] + p * plane, hp, plane * sizeof(float),
+                         cudaMemcpyHostToDevice, ctx->copy_stream));
+      ctx->h2d += (int64_t)(plane * sizeof(float));
+      planes[p] = ctx->d_stage[b] + p * plane;
+    }
   }
   CK(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
-  CKL(launch_pack_forcing(ctx->copy_stream, ctx->d_stage[b], nd, ctx->ngrid, ctx->d_cell_xy,
-                          ctx->dev.nc, ctx->dev.ncs, d_out));
+  CKL(launch_pack_forcing(ctx->copy_stream, planes, nd, ctx->ngrid, ctx->d_cell_xy, ctx->dev.nc,
+                          ctx->dev.ncs, d_out));
   return 0;
 }
 
@@ -312,6 +337,14 @@ int h9_create(h9_ctx** out, int device_id) {
   }
   const char* td = getenv("H9_TILE_DAYS");
   if (td && atoi(td) > 0) ctx->tile_days = atoi(td);
+  const char* ing = getenv("H9_INGEST");
+  if (ing && !strcmp(ing, "gather")) ctx->ingest = 0;
+  if (ing && !strcmp(ing, "pack")) ctx->ingest = 1;
+  if (ing && !strcmp(ing, "hostread")) ctx->ingest = 3;
+  if (ing && !strcmp(ing, "zerocopy")) {
+    ctx->ingest = 2;
+    ctx->zero_copy = true;
+  }
   const char* bl = getenv("H9_BLOCK");
   if (bl && (atoi(bl) == 2000 || atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
   *out = ctx;
@@ -568,7 +601,7 @@ int h9_run_days_device(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day,
   if (ndays == 0) return H9_OK;
   if (set_device(ctx)) return H9_ERR_CUDA;
   if (upload_year_index(ctx, ndays, year_index_of_day)) return H9_ERR_CUDA;
-  if (launch_days(ctx, ndays, ctx->d_year_index, d_forcing, day_stride, plane_stride))
+  if (launch_days(ctx, ndays, ctx->d_year_index, strided_view(d_forcing, day_stride, plane_stride)))
     return H9_ERR_CUDA;
   advance_years(ctx, ndays, year_index_of_day);
   uint32_t any = 0;
@@ -593,8 +626,31 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
   const size_t day_stride = (size_t)kForcingPlanes * ctx->dev.ncs;
   const int td = ctx->tile_days;
   const int ntiles = (ndays + td - 1) / td;
-  /* two-deep pipeline: tile k+1 is copied and packed on the copy stream while
-   * tile k is stepped on the compute stream */
+  /* Pageable host arrays (or H9_INGEST=gather): two-deep pipeline, tile k+1 is copied on the
+   * copy stream (copy engine, no SM) while tile k is stepped on the compute stream; the
+   * stepping kernel reads the grid tile exactly as the host holds it, through the land
+   * index.  The alternatives with a separate compaction pass (H9_INGEST=pack, =zerocopy) were
+   * measured slower: the stepping kernel owns every register of every SM, so any second
+   * kernel queues behind it.  Measured on a B200, 0.5 deg year: hostread 65.8 ms, gather
+   * 69.1 ms (PCIe-bound: the whole grid, 2.65 GB, crosses the bus), pack 68.4, zerocopy 71.6. */
+  if (ctx->ingest == 3 && pinned) {
+    /* hostread: no copies at all.  The stepping kernel loads each day's seven values for
+     * its cell straight from the host's page-locked arrays (mapped into the device address
+     * space), one day ahead of use; only the land cells' values cross PCIe. */
+    ForcingView fv;
+    for (int p = 0; p < kForcingPlanes; ++p) {
+      void* dp = nullptr;
+      CK(cudaHostGetDevicePointer(&dp, (void*)src[p], 0));
+      fv.plane[p] = (const float*)dp;
+    }
+    fv.day_stride = ctx->ngrid;
+    if (launch_days(ctx, ndays, ctx->d_year_index, fv, ctx->d_cell_xy)) return H9_ERR_CUDA;
+    ctx->h2d += (int64_t)ndays * kForcingPlanes * ctx->dev.nc * (int64_t)sizeof(float);
+    advance_years(ctx, ndays, year_index_of_day);
+    uint32_t any_hr = 0;
+    if (read_any_fault(ctx, &any_hr)) return H9_ERR_CUDA;
+    return (int)any_hr;
+  }
   for (int k = 0; k < ntiles; ++k) {
     const int b = k & 1;
     const int d0 = k * td, nd = std::min(td, ndays - d0);
@@ -602,12 +658,32 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
       CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
       if (!pinned) CK(cudaEventSynchronize(ctx->ev_h2d[b])); /* h_stage[b] is free again */
     }
-    if (stage_and_pack(ctx, b, d0, nd, src, pinned, ctx->d_packed[b])) return H9_ERR_CUDA;
-    CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
-    if (launch_days(ctx, nd, ctx->d_year_index + d0, ctx->d_packed[b], day_stride,
-                    (size_t)ctx->dev.ncs))
-      return H9_ERR_CUDA;
+    if (ctx->ingest == 0 || ctx->ingest == 3) { /* gather: H2D only */
+      const size_t plane = (size_t)nd * ctx->ngrid;
+      for (int p = 0; p < kForcingPlanes; ++p) {
+        const float* hp = src[p] + (size_t)d0 * ctx->ngrid;
+        if (!pinned) {
+          memcpy(ctx->h_stage[b] + p * plane, hp, plane * sizeof(float));
+          hp = ctx->h_stage[b] + p * plane;
+        }
+        CK(cudaMemcpyAsync(ctx->d_stage[b] + p * plane, hp, plane * sizeof(float),
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->h2d += (int64_t)(plane * sizeof(float));
+      }
+      CK(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
+      if (launch_days(ctx, nd, ctx->d_year_index + d0, strided_view(ctx->d_stage[b], ctx->ngrid, plane),
+                      ctx->d_cell_xy))
+        return H9_ERR_CUDA;
+    } else {
+      if (stage_and_pack(ctx, b, d0, nd, src, pinned, ctx->d_packed[b])) return H9_ERR_CUDA;
+      CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
+      if (launch_days(ctx, nd, ctx->d_year_index + d0,
+                      strided_view(ctx->d_packed[b], day_stride, (size_t)ctx->dev.ncs)))
+        return H9_ERR_CUDA;
+    }
     CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
     advance_years(ctx, nd, year_index_of_day + d0);
   }
@@ -808,10 +884,10 @@ int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const fl
   diag.w_imbalance = ctx->d_diag + 11 * n;
   diag.jwt = (int32_t*)(ctx->d_diag + 12 * n);
   if (ctx->math_mode == H9_MATH_EXACT) {
-    CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, ctx->d_step_forcing, n,
+    CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
                                     ctx->step_counter, diag));
   } else {
-    CKL(launch_hydrology_step_fast(ctx->stream, d, ctx->geo, ctx->d_step_forcing, n,
+    CKL(launch_hydrology_step_fast(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
                                    ctx->step_counter, diag));
   }
   ctx->step_counter += 1;

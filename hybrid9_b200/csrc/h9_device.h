@@ -22,6 +22,14 @@ constexpr int kCellPad = 128;      /* ncs is a multiple of this */
 constexpr int kAnnualPlanes = 13;  /* npp, plant_mass, rnf, evap, theta_total, theta(1..8) */
 constexpr int kForcingPlanes = 7;  /* tas, rlds, rsds, huss, ps, pr, rhs (READ_PGF.f90 order) */
 
+/* the seven forcing fields of one batch of days: plane[k][d*day_stride + cell].  The planes
+ * may be slices of one compact device buffer, of a staged grid tile, or the host's own
+ * page-locked arrays mapped into the device address space (read in place over PCIe). */
+struct ForcingView {
+  const float* plane[kForcingPlanes];
+  size_t day_stride;
+};
+
 struct DevArrays {
   int nc;  /* land cells of this ctx */
   int ncs; /* padded cell stride */
@@ -63,11 +71,12 @@ struct GrowDiagArrays {
  * All return the cudaError_t of the launch as int. */
 #define H9_DECLARE_LAUNCHERS(SUFFIX)                                                             \
   int launch_days_##SUFFIX(void* stream, const DevArrays& a, const Geo& g, int ndays,            \
-                           const int32_t* d_year_index, const float* d_forcing,                  \
-                           size_t day_stride, size_t plane_stride, int cur_year, int nt,         \
-                           unsigned long long step0, int block);                                 \
+                           const int32_t* d_year_index, const ForcingView& fv,                   \
+                           int cur_year, int nt,                                                 \
+                           unsigned long long step0, int block,                                  \
+                           const int32_t* d_cell_index /* nullptr: compact forcing */);          \
   int launch_hydrology_step_##SUFFIX(void* stream, const DevArrays& a, const Geo& g,             \
-                                     const float* d_forcing, size_t plane_stride,                \
+                                     const ForcingView& fv,                                      \
                                      unsigned long long step0, const StepDiagArrays& diag);      \
   int launch_grow_day_##SUFFIX(void* stream, const DevArrays& a, const Geo& g,                   \
                                const float* d_tas, const GrowDiagArrays& diag);
@@ -76,8 +85,8 @@ H9_DECLARE_LAUNCHERS(exact)
 H9_DECLARE_LAUNCHERS(fast)
 
 /* mode-independent kernels, h9_pack.cu */
-int launch_pack_forcing(void* stream, const float* d_grid /* [7][ndays][ngrid] */, int ndays,
-                        size_t ngrid, const int32_t* d_cell_xy, int nc, int ncs,
+int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes] /* each [ndays][ngrid] */,
+                        int ndays, size_t ngrid, const int32_t* d_cell_xy, int nc, int ncs,
                         float* d_out /* [ndays][7][ncs] */);
 int launch_clear_u32(void* stream, uint32_t* p, size_t n, uint32_t v);
 

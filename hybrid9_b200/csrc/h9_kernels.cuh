@@ -77,15 +77,15 @@ __device__ __forceinline__ void store_grow_state(const DevArrays& a, int c, cons
   a.rdepth[c] = s.rdepth;
 }
 
-__device__ __forceinline__ Forcing load_forcing(const float* f, size_t plane_stride) {
+__device__ __forceinline__ Forcing load_forcing(const ForcingView& fv, size_t off) {
   Forcing r;
-  r.tas = __ldg(f);
-  r.rlds = __ldg(f + plane_stride);
-  r.rsds = __ldg(f + 2 * plane_stride);
-  r.huss = __ldg(f + 3 * plane_stride);
-  r.ps = __ldg(f + 4 * plane_stride);
-  r.pr = __ldg(f + 5 * plane_stride);
-  r.rhs = __ldg(f + 6 * plane_stride);
+  r.tas = __ldg(fv.plane[0] + off);
+  r.rlds = __ldg(fv.plane[1] + off);
+  r.rsds = __ldg(fv.plane[2] + off);
+  r.huss = __ldg(fv.plane[3] + off);
+  r.ps = __ldg(fv.plane[4] + off);
+  r.pr = __ldg(fv.plane[5] + off);
+  r.rhs = __ldg(fv.plane[6] + off);
   return r;
 }
 
@@ -105,9 +105,8 @@ __device__ __forceinline__ void record_fault(const DevArrays& a, int c, uint32_t
 template <class M, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
-            const int32_t* __restrict__ year_index, const float* __restrict__ forcing,
-            size_t day_stride, size_t plane_stride, int cur_year, int nt,
-            unsigned long long step0) {
+            const int32_t* __restrict__ year_index, const ForcingView fv, int cur_year, int nt,
+            unsigned long long step0, const int32_t* __restrict__ cell_index) {
   const int c = blockIdx.x * BLOCK + threadIdx.x;
   if (c >= a.nc) return;
 
@@ -122,15 +121,17 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   load8(a.theta_sum, c, theta_sum);
   uint32_t sticky = a.fault[c];
 
-  const float* fcell = forcing + c;
-  Forcing fnext = load_forcing(fcell, plane_stride);
+  /* compact forcing [day][7][ncs] (cell_index == nullptr) or the grid tile as the host holds
+   * it, gathered through the land index */
+  const size_t fcell = (size_t)(cell_index ? __ldg(cell_index + c) : c);
+  Forcing fnext = load_forcing(fv, fcell);
   int iy_next = __ldg(year_index);
 
   for (int d = 0; d < ndays; ++d) {
     const Forcing f = fnext;
     const int iy = iy_next;
     if (d + 1 < ndays) { /* prefetch the next day's forcing behind this day's 48 sub-steps */
-      fnext = load_forcing(fcell + (size_t)(d + 1) * day_stride, plane_stride);
+      fnext = load_forcing(fv, fcell + (size_t)(d + 1) * fv.day_stride);
       iy_next = __ldg(year_index + d + 1);
     }
     if (iy != cur_year) { /* HYBRID9.f90:134-146 */
@@ -195,8 +196,7 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
 
 template <class M>
 __global__ void __launch_bounds__(128)
-hydrology_step_kernel(const DevArrays a, const __grid_constant__ Geo g,
-                      const float* __restrict__ forcing, size_t plane_stride,
+hydrology_step_kernel(const DevArrays a, const __grid_constant__ Geo g, const ForcingView fv,
                       unsigned long long step0, const StepDiagArrays diag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
@@ -205,7 +205,7 @@ hydrology_step_kernel(const DevArrays a, const __grid_constant__ Geo g,
   load_params(a, c, p);
   load_state(a, c, s);
   uint32_t sticky = a.fault[c];
-  const Forcing f = load_forcing(forcing + c, plane_stride);
+  const Forcing f = load_forcing(fv, (size_t)c);
   Day day;
   day_setup<M>(g, f, s.lai, s.lai_litter, day);
   StepOut so;
@@ -244,8 +244,8 @@ grow_day_kernel(const DevArrays a, const __grid_constant__ Geo g, const float* _
 
 template <class M>
 int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
-                  const int32_t* d_year_index, const float* d_forcing, size_t day_stride,
-                  size_t plane_stride, int cur_year, int nt, unsigned long long step0, int block) {
+                  const int32_t* d_year_index, const ForcingView& fv, int cur_year, int nt,
+                  unsigned long long step0, int block, const int32_t* d_cell_index) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a.nc <= 0 || ndays <= 0) return 0;
   /* block: threads per block (32/64/128) + 1000 when the kernel variant capped at 128
@@ -255,7 +255,7 @@ int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
   const int bs = block >= 2000 ? 64 : block % 1000;
 #define H9_LAUNCH(BS, MINB)                                                                      \
   days_kernel<M, BS, MINB><<<(a.nc + BS - 1) / BS, BS, 0, st>>>(                                 \
-      a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0)
+      a, g, ndays, d_year_index, fv, cur_year, nt, step0, d_cell_index)
   if (bs == 32) {
     if (capped) H9_LAUNCH(32, 16); else H9_LAUNCH(32, 1);
   } else if (bs == 128) {
@@ -269,11 +269,11 @@ int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
 
 template <class M>
 int launch_hydrology_step_t(void* stream, const DevArrays& a, const Geo& g,
-                            const float* d_forcing, size_t plane_stride,
-                            unsigned long long step0, const StepDiagArrays& diag) {
+                            const ForcingView& fv, unsigned long long step0,
+                            const StepDiagArrays& diag) {
   if (a.nc <= 0) return 0;
   hydrology_step_kernel<M><<<(a.nc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      a, g, d_forcing, plane_stride, step0, diag);
+      a, g, fv, step0, diag);
   return (int)cudaGetLastError();
 }
 
@@ -287,16 +287,17 @@ int launch_grow_day_t(void* stream, const DevArrays& a, const Geo& g, const floa
 
 #define H9_DEFINE_LAUNCHERS(SUFFIX, POLICY)                                                      \
   int launch_days_##SUFFIX(void* stream, const DevArrays& a, const Geo& g, int ndays,            \
-                           const int32_t* d_year_index, const float* d_forcing,                  \
-                           size_t day_stride, size_t plane_stride, int cur_year, int nt,         \
-                           unsigned long long step0, int block) {                                \
-    return launch_days_t<POLICY>(stream, a, g, ndays, d_year_index, d_forcing, day_stride,       \
-                                 plane_stride, cur_year, nt, step0, block);                      \
+                           const int32_t* d_year_index, const ForcingView& fv,                   \
+                           int cur_year, int nt,                                                 \
+                           unsigned long long step0, int block,                                  \
+                           const int32_t* d_cell_index) {                                        \
+    return launch_days_t<POLICY>(stream, a, g, ndays, d_year_index, fv, cur_year, nt, step0,     \
+                                 block, d_cell_index);                                           \
   }                                                                                              \
   int launch_hydrology_step_##SUFFIX(void* stream, const DevArrays& a, const Geo& g,             \
-                                     const float* d_forcing, size_t plane_stride,                \
+                                     const ForcingView& fv,                                      \
                                      unsigned long long step0, const StepDiagArrays& diag) {     \
-    return launch_hydrology_step_t<POLICY>(stream, a, g, d_forcing, plane_stride, step0, diag);  \
+    return launch_hydrology_step_t<POLICY>(stream, a, g, fv, step0, diag);                       \
   }                                                                                              \
   int launch_grow_day_##SUFFIX(void* stream, const DevArrays& a, const Geo& g,                   \
                                const float* d_tas, const GrowDiagArrays& diag) {                 \

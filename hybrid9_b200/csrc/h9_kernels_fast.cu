@@ -17,9 +17,9 @@ namespace h9 {
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
-                 const int32_t* __restrict__ year_index, const float* __restrict__ forcing,
-                 size_t day_stride, size_t plane_stride, int cur_year, int nt,
-                 unsigned long long step0, int cells_per_block) {
+                 const int32_t* __restrict__ year_index, const ForcingView fv, int cur_year,
+                 int nt, unsigned long long step0, int cells_per_block,
+                 const int32_t* __restrict__ cell_index) {
   extern __shared__ float smem[];
   /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells */
   const int c = blockIdx.x * cells_per_block + threadIdx.x;
@@ -44,15 +44,17 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   }
   uint32_t sticky = a.fault[c];
 
-  const float* fcell = forcing + c;
-  Forcing fnext = load_forcing(fcell, plane_stride);
+  /* compact forcing [day][7][ncs], or the grid tile as the host holds it gathered through
+   * the land index (no separate pack pass on the h9_run_days pipeline) */
+  const size_t fcell = (size_t)(cell_index ? __ldg(cell_index + c) : c);
+  Forcing fnext = load_forcing(fv, fcell);
   int iy_next = __ldg(year_index);
 
   for (int d = 0; d < ndays; ++d) {
     const Forcing f = fnext;
     const int iy = iy_next;
     if (d + 1 < ndays) { /* prefetch the next day's forcing behind this day's sub-steps */
-      fnext = load_forcing(fcell + (size_t)(d + 1) * day_stride, plane_stride);
+      fnext = load_forcing(fv, fcell + (size_t)(d + 1) * fv.day_stride);
       iy_next = __ldg(year_index + d + 1);
     }
     const bool new_year = (iy != cur_year); /* HYBRID9.f90:134-146 */
@@ -137,8 +139,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
 }
 
 __global__ void __launch_bounds__(128)
-hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g,
-                           const float* __restrict__ forcing, size_t plane_stride,
+hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, const ForcingView fv,
                            unsigned long long step0, const StepDiagArrays diag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
@@ -159,7 +160,7 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g,
   s.wa = gs.wa;
   s.rnf_sum = gs.rnf_sum;
   uint32_t sticky = a.fault[c];
-  const Forcing f = load_forcing(forcing + c, plane_stride);
+  const Forcing f = load_forcing(fv, (size_t)c);
   DayFast day;
   float tas;
   day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
@@ -190,9 +191,8 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g,
 }
 
 int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
-                     const int32_t* d_year_index, const float* d_forcing, size_t day_stride,
-                     size_t plane_stride, int cur_year, int nt, unsigned long long step0,
-                     int block) {
+                     const int32_t* d_year_index, const ForcingView& fv, int cur_year, int nt,
+                     unsigned long long step0, int block, const int32_t* d_cell_index) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a.nc <= 0 || ndays <= 0) return 0;
   /* block: threads per block (32/64/128), +1000 for the <=128-register variant;
@@ -210,7 +210,7 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
     if (e != cudaSuccess) return (int)e;
     days_kernel_fast<512, 1><<<(a.nc + cpb - 1) / cpb, threads, shm, st>>>(
-        a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0, cpb);
+        a, g, ndays, d_year_index, fv, cur_year, nt, step0, cpb, d_cell_index);
     return (int)cudaGetLastError();
   }
   const bool capped = block >= 1000;
@@ -222,7 +222,7 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
     if (e != cudaSuccess) return (int)e;                                                       \
     days_kernel_fast<BS, MINB><<<(a.nc + BS - 1) / BS, BS, shm, st>>>(                         \
-        a, g, ndays, d_year_index, d_forcing, day_stride, plane_stride, cur_year, nt, step0, BS);  \
+        a, g, ndays, d_year_index, fv, cur_year, nt, step0, BS, d_cell_index);                 \
   } while (0)
   if (bs == 32) {
     if (capped) H9_LAUNCH(32, 16); else H9_LAUNCH(32, 1);
@@ -236,11 +236,11 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
 }
 
 int launch_hydrology_step_fast(void* stream, const DevArrays& a, const Geo& g,
-                               const float* d_forcing, size_t plane_stride,
-                               unsigned long long step0, const StepDiagArrays& diag) {
+                               const ForcingView& fv, unsigned long long step0,
+                               const StepDiagArrays& diag) {
   if (a.nc <= 0) return 0;
   hydrology_step_kernel_fast<<<(a.nc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      a, g, d_forcing, plane_stride, step0, diag);
+      a, g, fv, step0, diag);
   return (int)cudaGetLastError();
 }
 

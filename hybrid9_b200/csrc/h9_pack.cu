@@ -1,9 +1,11 @@
 /*
  * h9_pack.cu -- K4: forcing ingest.  The host hands over the seven PGF arrays
  * exactly as READ_PGF leaves them, (lon_c,lat_c,ndays) with x fastest and the
- * day slowest (READ_NET_CDF_3DR.f90:95-97); a tile of days of each is copied to
- * the device as is, and this kernel does the land compaction and the
- * (x,y,day) -> [day][field][cell] re-layout the time-stepping kernel streams.
+ * day slowest (READ_NET_CDF_3DR.f90:95-97).  This kernel does the land compaction and
+ * the (x,y,day) -> [day][field][cell] re-layout the time-stepping kernel streams.  When
+ * the host arrays are page-locked it reads them in place over PCIe (zero-copy gather:
+ * only the land cells, about a quarter of the grid, cross the bus); pageable arrays are
+ * first copied tile by tile through a pinned staging ring.
  */
 #include <cuda_runtime.h>
 
@@ -13,28 +15,34 @@
 
 namespace h9 {
 
+struct PackSrc {
+  const float* plane[kForcingPlanes]; /* each (ndays, ngrid): device memory or mapped pinned host memory */
+};
+
 __global__ void __launch_bounds__(256)
-pack_forcing_kernel(const float* __restrict__ grid, int ndays, size_t ngrid,
+pack_forcing_kernel(const PackSrc src, int ndays, size_t ngrid,
                     const int32_t* __restrict__ cell_xy, int nc, int ncs,
                     float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int d = blockIdx.y;
   if (c >= ncs) return;
   /* padding cells replicate the last land cell so that staged tiles hold finite data */
-  const int src = cell_xy[c < nc ? c : nc - 1];
+  const int cell = cell_xy[c < nc ? c : nc - 1];
+  float v[kForcingPlanes];
 #pragma unroll
-  for (int p = 0; p < kForcingPlanes; ++p) {
-    const float v = __ldg(grid + ((size_t)p * ndays + d) * ngrid + src);
-    out[((size_t)d * kForcingPlanes + p) * ncs + c] = v;
-  }
+  for (int p = 0; p < kForcingPlanes; ++p) v[p] = __ldg(src.plane[p] + (size_t)d * ngrid + cell);
+#pragma unroll
+  for (int p = 0; p < kForcingPlanes; ++p) out[((size_t)d * kForcingPlanes + p) * ncs + c] = v[p];
 }
 
-int launch_pack_forcing(void* stream, const float* d_grid, int ndays, size_t ngrid,
-                        const int32_t* d_cell_xy, int nc, int ncs, float* d_out) {
+int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes], int ndays,
+                        size_t ngrid, const int32_t* d_cell_xy, int nc, int ncs, float* d_out) {
   if (nc <= 0 || ndays <= 0) return 0;
+  PackSrc src;
+  for (int p = 0; p < kForcingPlanes; ++p) src.plane[p] = planes[p];
   dim3 grid((ncs + 255) / 256, ndays);
-  pack_forcing_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_grid, ndays, ngrid, d_cell_xy, nc,
-                                                              ncs, d_out);
+  pack_forcing_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ndays, ngrid, d_cell_xy, nc, ncs,
+                                                              d_out);
   return (int)cudaGetLastError();
 }
 

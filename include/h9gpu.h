@@ -123,7 +123,10 @@ int h9_get_state(h9_ctx* ctx, float* h2osoi_liq, float* zwt, float* wa, float* l
  * GROW (:217), daily/annual accumulators (:235-254).
  * year_index_of_day[d] = iY (1-based year within the run, HYBRID9.f90:269) of day d;
  * tas,rlds,rsds,huss,ps,pr,rhs: (lon_c,lat_c,ndays) exactly as READ_PGF leaves them.
- * Host pointers may be pageable or pinned (h9_host_alloc); pinned is faster.
+ * Host pointers may be pageable or page-locked (h9_host_alloc).  Page-locked arrays
+ * are not copied at all: the stepping kernel reads each day's values for its land
+ * cells in place over PCIe, one day ahead of use (only ~26 % of a global grid is
+ * land).  Pageable arrays are copied tile by tile through a pinned ring.
  * Returns 0, or >0 (fault bits) if any cell faulted -- the caller then reads
  * h9_get_fault and STOPs like the reference. */
 int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const float* tas,
