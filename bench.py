@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--grid", default="0.5", choices=["0.5", "0.25", "regional", "tiny"])
+    ap.add_argument("--grid", default="0.5", choices=["0.5", "0.25", "regional", "tiny", "band8"])
     ap.add_argument("--days", type=int, default=365)
     ap.add_argument("--nisurf", type=int, default=48)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
@@ -73,6 +73,9 @@ def grid_spec(name):
         # continents are not Earth's, so the window is placed where it holds 2,500 land cells
         return dict(nx=720, ny=360, n_land=67420, label="regional 100x74 window of the 0.5deg mask "
                     "(2,500 land cells)", window=synth_regional_window())
+    if name == "band8":
+        return dict(nx=720, ny=360, n_land=67420, band=(0, 8),
+                    label="first of 8 latitude bands of the 0.5deg mask (one GPU's share of an 8-GPU strong-scaling run)")
     return dict(nx=72, ny=36, n_land=674, label="tiny 5deg test grid")
 
 
@@ -185,6 +188,9 @@ def build_world(args):
     w = synth.make_world(nx=g["nx"], ny=g["ny"], n_land=g["n_land"], seed=9)
     if "window" in g:
         w = w.window(*g["window"])
+    if "band" in g:
+        from hybrid9_b200 import distributed as h9d
+        w = h9d.shard_world(w, g["band"][0], g["band"][1])[0]
     return w, g["label"]
 
 
@@ -294,7 +300,10 @@ def main():
 
     def collective(iy):
         if multi:
-            h9d.h9_annual_collective(h, iy, n_land_all, device=dev)
+            parts, budget = h9d.h9_annual_collective(h, iy, n_land_all, device=dev)
+            if year[0] <= 1:  # sanity of the gathered view, outside the hot loop's steady state
+                assert [int(p.shape[1]) for p in parts] == n_land_all
+                assert int(round(float(budget[5]))) == sum(n_land_all) and float(budget[7]) == 0.0
 
     def step_device():
         year[0] += 1

@@ -251,7 +251,9 @@ int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
   /* block: threads per block (32/64/128) + 1000 when the kernel variant capped at 128
    * registers per thread (16 warps per SM resident: the whole 0.5 deg grid in one wave) is
    * wanted instead of the uncapped one (255 registers, 8 warps per SM) */
-  const bool capped = block >= 1000 && block < 2000;
+  /* the generic (exact-mode) kernel needs its registers for the double-precision pow/exp/log:
+   * the 128-register cap doubles its run time, so it is only honoured on explicit request */
+  const bool capped = block >= 1000 && block < 2000 && block != 1064;
   const int bs = block >= 2000 ? 64 : block % 1000;
 #define H9_LAUNCH(BS, MINB)                                                                      \
   days_kernel<M, BS, MINB><<<(a.nc + BS - 1) / BS, BS, 0, st>>>(                                 \

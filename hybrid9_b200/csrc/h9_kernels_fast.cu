@@ -213,7 +213,14 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
         a, g, ndays, d_year_index, fv, cur_year, nt, step0, cpb, d_cell_index);
     return (int)cudaGetLastError();
   }
-  const bool capped = block >= 1000;
+  /* the default (1064) adapts to the shard size: up to 8 warps per SM the uncapped variant
+   * (more registers, more instruction-level parallelism per warp) is faster; above that the
+   * 128-register variant keeps the whole shard resident in one wave.  Same PTX, same results. */
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const bool small_shard = (block == 1064) && (a.nc <= nsm * 8 * 32);
+  const bool capped = block >= 1000 && !small_shard;
   const int bs = block % 1000;
 #define H9_LAUNCH(BS, MINB)                                                                    \
   do {                                                                                         \

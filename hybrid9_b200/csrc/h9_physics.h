@@ -22,7 +22,7 @@
  * reference's operation order with IEEE division (its translation unit is
  * built with -fmad=false) and computes pow/exp/log with portable double-precision
  * kernels that give the same bits on the GPU and on a host build; MathFast uses
- * MUFU ex2/lg2/rcp and lets the compiler contract multiply-adds.
+ * MUFU ex2/lg2/rcp (its sub-step lives in h9_physics_fast.cuh with explicit FMAs).
  *
  * The header is plain C++ so that tests/twin can compile the very same source
  * for the host and diff it against the oracle without a GPU.

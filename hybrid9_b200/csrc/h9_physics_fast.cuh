@@ -181,7 +181,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
    * denominator Rs*Rc + Rs*Ra + Rc*Ra */
   const float RsRc = Rs * Rc, RsRa = Rs * d.Ra, RcRa = Rc * d.Ra;
   const float invD = MathFast::rcp(RsRc + RsRa + RcRa);
-  const float LE = ((RsRc + RsRa) * PMc + (RsRc + RcRa) * PMs) * invD;
+  const float LE = fmaf(RsRc + RsRa, PMc, (RsRc + RcRa) * PMs) * invD;
   const float VDD0 = fmaf(d.A - d.dg * LE, d.raa_inv_rhocp, d.VDD);
   const float rv = d.rhocp * VDD0;
   const float LEc = fmaf(rv, d.inv_rac, d.lec_a) * MathFast::rcp(fmaf(d.gamma, fmaf(rsc, d.inv_rac, 1.0f), d.desatdT));
@@ -190,7 +190,8 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   float qflx_evap_grnd = LEs * d.k_lamb;
 
   /* evaporation limit :396-400 */
-  const float evap_max1 = fmaxf(0.0f, g.dz[1] * (theta[0] - kWatmin) * rdt - qflx_tran_veg_col * c.rootr(0));
+  const float evap_max1 =
+      fmaxf(0.0f, fmaf(-qflx_tran_veg_col, c.rootr(0), g.dz[1] * (theta[0] - kWatmin) * rdt));
   qflx_evap_grnd = fminf(evap_max1, qflx_evap_grnd);
 
   /* Infiltration :426-478 */
@@ -299,7 +300,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   float dwat2[NL + 1], gam[NL + 1];
   float bet, rbet, minpiv;
   {
-    const float rmx = (qflx_infl - q[0]) - qflx_tran_veg_col * c.rootr(0);
+    const float rmx = fmaf(-qflx_tran_veg_col, c.rootr(0), qflx_infl - q[0]);
     bet = g.dzdt[1] + qa[0];
     if (bet == 0.0f) fault |= FAULT_PIVOT1;
     rbet = MathFast::rcp(bet);
@@ -308,7 +309,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   }
 #pragma unroll
   for (int i = 1; i < NL; ++i) {
-    const float rmx = (q[i - 1] - q[i]) - qflx_tran_veg_col * c.rootr(i);
+    const float rmx = fmaf(-qflx_tran_veg_col, c.rootr(i), q[i - 1] - q[i]);
     const float amx = -qa[i - 1];
     const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
     gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
@@ -320,7 +321,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   { /* aquifer row */
     const float rmx = q[NL - 1];
     const float amx = -qa[NL - 1];
-    const float bmx = dz9 * rdt - qb[NL - 1];
+    const float bmx = fmaf(dz9, rdt, -qb[NL - 1]);
     gam[NL] = qb[NL - 1] * rbet;
     bet = fmaf(-amx, gam[NL], bmx);
     minpiv = fminf(minpiv, fabsf(bet));
@@ -359,7 +360,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   float rous = fast_specific_yield(c, NL - 1, zwtmm);
   if (jwt == NL) {
     s.wa = fmaf(qcharge, dt, s.wa);
-    s.zwt -= qcharge * dt * 0.001f * MathFast::rcp(rous);
+    s.zwt = fmaf(-(qcharge * dt * 0.001f), MathFast::rcp(rous), s.zwt);
   } else { /* zwtmm stays the stale value of :492 inside the loops */
     float qcharge_tot = qcharge * dt;
     if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
@@ -393,7 +394,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   rous = fast_specific_yield(c, NL - 1, zwtmm);
   if (jwt == NL) { /* jwt is not recomputed on this path */
     s.wa = fmaf(-rsub_top, dt, s.wa);
-    s.zwt += rsub_top * dt * 0.001f * MathFast::rcp(rous);
+    s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
     s.h2o[NL - 1] += fmaxf(0.0f, s.wa - 5000.0f);
     s.wa = fminf(s.wa, 5000.0f);
   } else {
@@ -425,7 +426,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   /* excess cascade :1131-1152: a no-op unless some layer is above its capacity */
   float over = s.h2o[0] - fmaxf(0.0f, c.ths(0) * g.dz[1]);
 #pragma unroll
-  for (int i = 1; i < NL; ++i) over = fmaxf(over, s.h2o[i] - fmaxf(0.01f, c.ths(i)) * g.dz[i + 1]);
+  for (int i = 1; i < NL; ++i) over = fmaxf(over, fmaf(-fmaxf(0.01f, c.ths(i)), g.dz[i + 1], s.h2o[i]));
   float qflx_rsub_sat = 0.0f;
   if (over > 0.0f) {
 #pragma unroll
@@ -483,7 +484,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   /* :1282-1283 */
   const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
-  s.rnf_sum = (s.rnf_sum + r1) + r2;
+  s.rnf_sum = fmaf(rsub_top, dt, fmaf(qflx_surf, dt, s.rnf_sum));
 
   o.qflx_tran_veg_col = qflx_tran_veg_col;
   o.qflx_evap_grnd = qflx_evap_grnd;
