@@ -146,24 +146,23 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   float theta[NL];
 
   /* :141-151 */
-  float w0 = d.rain_dt + s.wa;
 #pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    w0 += s.h2o[i];
-    theta[i] = s.h2o[i] * g.rdzw[i + 1];
-  }
+  for (int i = 0; i < NL; ++i) theta[i] = s.h2o[i] * g.rdzw[i + 1];
+  /* column sums as a pairwise tree: 3 dependent adds instead of 8 */
+  const float w0 = (d.rain_dt + s.wa) + (((s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3])) +
+                                         ((s.h2o[4] + s.h2o[5]) + (s.h2o[6] + s.h2o[7])));
 
   /* SurfaceRunoff :182-212 */
   const float fsat = c.fmax() * MathFast::ex2((-0.5f * kFff * kLog2e) * s.zwt);
   float qflx_surf = fsat * d.forc_rain;
 
   /* beta from the previous sub-step's smp :269-276: 1 - x/(-150000) == 1 + x/150000 */
-  float beta = 0.0f;
+  float bw[NL];
 #pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    const float b = __saturatef(fmaf(s.smp[i] - g.zc[i + 1], 1.0f / 150000.0f, 1.0f));
-    beta = fmaf(c.rootr(i), b, beta);
-  }
+  for (int i = 0; i < NL; ++i)
+    bw[i] = __saturatef(fmaf(s.smp[i] - g.zc[i + 1], 1.0f / 150000.0f, 1.0f));
+  const float beta = fmaf(c.rootr(0), bw[0], fmaf(c.rootr(1), bw[1], fmaf(c.rootr(2), bw[2], c.rootr(3) * bw[3]))) +
+                     fmaf(c.rootr(4), bw[4], fmaf(c.rootr(5), bw[5], fmaf(c.rootr(6), bw[6], c.rootr(7) * bw[7])));
 
   /* rsc :283-295, rss :325-331 */
   float rsc = (d.canopy_on && beta > 0.0f) ? d.rsc_num * MathFast::rcp(d.rsc_den0 * beta) : 1.0E6f;
@@ -227,26 +226,25 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
   }
-  zq[NL] = 0.0f;
-  if (deep) { /* :576-590: vol_eq(9) = A/(zwtmm-zi(8)) * (1 - (1+u)**e1), u = (zwtmm-zi(8))/(-psi) */
+  { /* :576-590: vol_eq(9) = A/(zwtmm-zi(8)) * (1 - (1+u)**e1), u = (zwtmm-zi(8))/(-psi).
+     * Evaluated for every cell and selected by `deep`: straight-line code schedules better
+     * than a divergent region, and most cells are deep */
     const int i = NL - 1;
     const float ths = c.ths(i), psi = c.psi(i), e1 = c.e1(i), inv_npsi = c.inv_npsi(i);
     const float u = (zwtmm - g.zi[NL]) * inv_npsi;
     /* r = ((1+u)**e1 - 1)/u.  The direct form loses every digit as the water table nears the
      * column base (u -> 0, where the reference's own float evaluation is noise); the
      * binomial series keeps r accurate there. */
-    float r;
-    if (u < 0.03f) {
-      const float a2 = 0.5f * (e1 - 1.0f), a3 = (1.0f / 3.0f) * (e1 - 2.0f), a4 = 0.25f * (e1 - 3.0f);
-      r = e1 * fmaf(u * a2, fmaf(u * a3, fmaf(u, a4, 1.0f), 1.0f), 1.0f);
-    } else {
-      r = (fast_pow(1.0f + u, e1) - 1.0f) * MathFast::rcp(u);
-    }
+    const float a2 = 0.5f * (e1 - 1.0f), a3 = (1.0f / 3.0f) * (e1 - 2.0f), a4 = 0.25f * (e1 - 3.0f);
+    const float r_series = e1 * fmaf(u * a2, fmaf(u * a3, fmaf(u, a4, 1.0f), 1.0f), 1.0f);
+    const float r_direct = (fast_pow(1.0f + u, e1) - 1.0f) * MathFast::rcp(u);
+    const float r = (u < 0.03f) ? r_series : r_direct;
     /* A/(zwtmm-zi(8)) * (1-temp0) = -A * inv_npsi * r */
     const float coefA = c.coef3(i) * (g.zi[NL] - g.zi[NL - 1]);
     float vol = -coefA * inv_npsi * r;
     vol = fminf(ths, fmaxf(vol, 0.0f));
-    zq[NL] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+    const float z9 = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+    zq[NL] = deep ? z9 : 0.0f;
   }
 
   /* hk, dhkdw, smp, dsmpdw :598-639 */
@@ -280,8 +278,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   }
   {
     const int i = NL - 1;
-    q[i] = qa[i] = qb[i] = 0.0f;
-    if (deep) {
+    {
       const float b = c.bsw(i), inv_ths = c.inv_ths(i);
       const float s_node = fminf(1.0f, fmaxf(0.5f * fmaf(theta[i], inv_ths, 1.0f), 0.01f));
       const float smp1 = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
@@ -290,9 +287,9 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
       const float rden = MathFast::rcp(zc9 - g.zc[NL]);
       const float num = (smp1 - s.smp[i]) - (zq[NL] - zq[i]);
       const float nd = num * dhkdw[i];
-      q[i] = -hk[i] * num * rden;
-      qa[i] = fmaf(hk[i], dsmpdw[i], -nd) * rden;
-      qb[i] = -fmaf(hk[i], dsmpdw1, nd) * rden;
+      q[i] = deep ? -hk[i] * num * rden : 0.0f;
+      qa[i] = deep ? fmaf(hk[i], dsmpdw[i], -nd) * rden : 0.0f;
+      qb[i] = deep ? -fmaf(hk[i], dsmpdw1, nd) * rden : 0.0f;
     }
   }
 
@@ -476,9 +473,9 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   rsub_top -= xs * rdt; /* :1211 */
 
   /* balance :1221-1244 */
-  float w1 = fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) w1 += s.h2o[i];
+  const float w1 =
+      fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa) +
+      (((s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3])) + ((s.h2o[4] + s.h2o[5]) + (s.h2o[6] + s.h2o[7])));
   const float imb = w1 - w0;
   if (!(fabsf(imb) <= 0.1f)) fault |= FAULT_IMBAL;
 
