@@ -132,3 +132,19 @@ def test_exact_mode_build_vs_oracle_tolerance(world):
     assert np.quantile(rel, 0.999) < 5e-5, np.quantile(rel, 0.999)
     assert (np.abs(a - b) <= 0.01 + 2e-3 * np.abs(b)).all(), rel.max()
     assert np.abs(tw.zwt[land] - ref.zwt[land]).max() < 2e-3
+
+
+@pytest.mark.parametrize("nisurf", [1, 24, 172])
+def test_other_substep_counts_bitexact(world, nisurf):
+    """dt = 86400/NISURF (INIT.f90:214; the reference's notes ran 1, 48 and 172)."""
+    w = world
+    f = synth.make_forcing(w, 2, seed=31)
+    o = make_oracle(w, nisurf=nisurf)
+    o.init_state()
+    st0 = o.get_state()
+    rc = o.run_days(np.ones(2, np.int32), f)
+    tw, ex = oracle_py.twin_run(w, st0, f, nisurf, synth.ZI_DRIVER, math="libm")
+    assert rc == int(np.bitwise_or.reduce(ex["fault"]))
+    ok = w.land.copy()
+    ok[w.land] = ex["fault"] == 0
+    assert_state_equal(tw, o.get_state(), ok)
