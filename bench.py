@@ -365,7 +365,7 @@ def main():
     peak, peak_src = peaks()
     achieved = units_rank * BYTES_PER_CELL_STEP / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "h9::days_kernel",
+                "frac": achieved / peak, "traffic": None, "kernel": "h9::days_kernel_fast" if args.math == "fast" else "h9::days_kernel<MathExact>",
                 "kernel_ms_per_launch": kern_ms, "launches_per_step": cnt["launches"] / args.steps,
                 "algorithmic_bytes_per_unit": BYTES_PER_CELL_STEP, "peak_source": peak_src,
                 "note": "algorithmic roofline of a per-sub-step operator; the fused kernel keeps "

@@ -40,6 +40,7 @@ struct h9_ctx {
    * 2 zerocopy pack */
   int ingest = 3;
   bool zero_copy = false;
+  int real_evap = 0; /* H9_OPT_REAL_EVAP */
   Geo geo;
   std::vector<int32_t> cell_xy;
   DevArrays dev;
@@ -125,6 +126,7 @@ void free_land(h9_ctx* ctx) {
   ctx->d_diag = nullptr;
   ctx->d_budget = nullptr;
   memset(&ctx->dev, 0, sizeof(ctx->dev));
+  ctx->dev.real_evap = ctx->real_evap;
   ctx->have_soil = false;
 }
 
@@ -402,6 +404,14 @@ int h9_set_math(h9_ctx* ctx, int mode) {
   return H9_OK;
 }
 
+int h9_set_option(h9_ctx* ctx, int option, int value) {
+  if (!ctx) return H9_ERR_ARG;
+  if (option != H9_OPT_REAL_EVAP) return fail(ctx, H9_ERR_ARG, "h9_set_option: unknown option");
+  ctx->real_evap = value ? 1 : 0;
+  ctx->dev.real_evap = ctx->real_evap;
+  return H9_OK;
+}
+
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block) {
   if (!ctx) return H9_ERR_ARG;
   if (tile_days > 0) ctx->tile_days = tile_days;
@@ -431,6 +441,7 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   d.nc = (int)ctx->cell_xy.size();
   d.ncs = std::max(kCellPad, (d.nc + kCellPad - 1) / kCellPad * kCellPad);
   d.nyr = ctx->nyr;
+  d.real_evap = ctx->real_evap;
   const size_t n = (size_t)d.ncs;
   int rc = 0;
   float *ths = nullptr, *hks = nullptr, *bs = nullptr, *ps = nullptr, *fm = nullptr;
@@ -455,6 +466,7 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   rc |= dev_alloc(ctx, &d.npp_sum, n);
   rc |= dev_alloc(ctx, &d.plant_mass_sum, n);
   rc |= dev_alloc(ctx, &d.h2osoi_sum_total, n);
+  rc |= dev_alloc(ctx, &d.evap_sum, n);
   rc |= dev_alloc(ctx, &d.theta_sum, n * NL);
   rc |= dev_alloc(ctx, &d.annual, (size_t)d.nyr * kAnnualPlanes * n);
   rc |= dev_alloc(ctx, &d.fault, n);
@@ -621,7 +633,6 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
   const float* src[7] = {tas, rlds, rsds, huss, ps, pr, rhs};
   bool pinned = true;
   for (int p = 0; p < 7; ++p) pinned = pinned && is_pinned(src[p]);
-  if (ensure_stage(ctx, !pinned)) return H9_ERR_CUDA;
   if (upload_year_index(ctx, ndays, year_index_of_day)) return H9_ERR_CUDA;
   const size_t day_stride = (size_t)kForcingPlanes * ctx->dev.ncs;
   const int td = ctx->tile_days;
@@ -651,6 +662,7 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
     if (read_any_fault(ctx, &any_hr)) return H9_ERR_CUDA;
     return (int)any_hr;
   }
+  if (ensure_stage(ctx, !pinned)) return H9_ERR_CUDA; /* staging buffers only on the copy paths */
   for (int k = 0; k < ntiles; ++k) {
     const int b = k & 1;
     const int d0 = k * td, nd = std::min(td, ndays - d0);

@@ -44,6 +44,8 @@ struct DevArrays {
   int32_t* nplants;
   /* annual accumulators of HYBRID9.f90:134-146 (per cell) */
   float *rnf_sum, *npp_sum, *plant_mass_sum, *h2osoi_sum_total; /* [ncs] */
+  float* evap_sum;   /* [ncs], only accumulated when real_evap != 0 (H9_OPT_REAL_EVAP) */
+  int real_evap;
   float* theta_sum;                                              /* [ncs][8] */
   /* annual means, HYBRID9.f90:263-291: [nyr][13][ncs] */
   float* annual;

@@ -120,6 +120,7 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   float theta_sum[NL];
   load8(a.theta_sum, c, theta_sum);
   uint32_t sticky = a.fault[c];
+  float evap_sum = a.real_evap ? a.evap_sum[c] : 0.0f;
 
   /* compact forcing [day][7][ncs] (cell_index == nullptr) or the grid tile as the host holds
    * it, gathered through the land index */
@@ -140,6 +141,7 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       npp_sum = 0.0f;
       plant_mass_sum = 0.0f;
       s.rnf_sum = 0.0f;
+      evap_sum = 0.0f;
       h2osoi_sum_total = 0.0f;
 #pragma unroll
       for (int i = 0; i < NL; ++i) theta_sum[i] = 0.0f;
@@ -154,6 +156,7 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       if (ft)
         record_fault(a, c, sticky, ft, step0 + (unsigned long long)d * g.nisurf + ns,
                      so.imbalance);
+      if (a.real_evap) evap_sum = evap_sum + (so.qflx_evap_grnd + so.qflx_tran_veg_col);
     }
 
     GrowOut go;
@@ -178,7 +181,8 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       out[0] = npp_sum;
       out[(size_t)1 * a.ncs] = M::div(plant_mass_sum, fnt);
       out[(size_t)2 * a.ncs] = M::div(s.rnf_sum, (float)(nt * g.nisurf));
-      out[(size_t)3 * a.ncs] = M::div(0.0f, (float)(nt * g.nisurf)); /* evap_sum never accumulates */
+      /* the reference's evap_sum never accumulates (axy_evap == 0) unless H9_OPT_REAL_EVAP */
+      out[(size_t)3 * a.ncs] = M::div(a.real_evap ? evap_sum : 0.0f, (float)(nt * g.nisurf));
       out[(size_t)4 * a.ncs] = M::div(h2osoi_sum_total, fnt);
 #pragma unroll
       for (int i = 0; i < NL; ++i) out[(size_t)(5 + i) * a.ncs] = M::div(theta_sum[i], fnt);
@@ -192,6 +196,7 @@ days_kernel(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   a.h2osoi_sum_total[c] = h2osoi_sum_total;
   store8(a.theta_sum, c, theta_sum);
   a.fault[c] = sticky;
+  if (a.real_evap) a.evap_sum[c] = evap_sum;
 }
 
 template <class M>

@@ -43,6 +43,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     s.rnf_sum = gs.rnf_sum;
   }
   uint32_t sticky = a.fault[c];
+  float evap_sum = a.real_evap ? a.evap_sum[c] : 0.0f;
 
   /* compact forcing [day][7][ncs], or the grid tile as the host holds it gathered through
    * the land index (no separate pack pass on the h9_run_days pipeline) */
@@ -62,6 +63,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       cur_year = iy;
       nt = 0;
       s.rnf_sum = 0.0f;
+      evap_sum = 0.0f;
     }
 
     DayFast day;
@@ -73,6 +75,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       const uint32_t ft = hydrology_step_fast(g, tbl, day, s, so);
       if (ft)
         record_fault(a, c, sticky, ft, step0 + (unsigned long long)d * g.nisurf + ns, so.imbalance);
+      if (a.real_evap) evap_sum += so.qflx_evap_grnd + so.qflx_tran_veg_col; /* H9_OPT_REAL_EVAP */
     }
 
     /* GROW (HYBRID9.f90:217): reads smp and rootr, rewrites rootr */
@@ -118,7 +121,8 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       out[0] = npp_sum;
       out[(size_t)1 * a.ncs] = plant_mass_sum * rnt;
       out[(size_t)2 * a.ncs] = s.rnf_sum * MathFast::rcp((float)(nt * g.nisurf));
-      out[(size_t)3 * a.ncs] = 0.0f; /* evap_sum never accumulates: axy_evap == 0 */
+      /* the reference's evap_sum never accumulates: axy_evap == 0 unless H9_OPT_REAL_EVAP */
+      out[(size_t)3 * a.ncs] = a.real_evap ? evap_sum * MathFast::rcp((float)(nt * g.nisurf)) : 0.0f;
       out[(size_t)4 * a.ncs] = h2osoi_sum_total * rnt;
 #pragma unroll
       for (int i = 0; i < NL; ++i) out[(size_t)(5 + i) * a.ncs] = theta_sum[i] * rnt;
@@ -136,6 +140,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   store_hydro_state(a, c, gs);
   store_grow_state(a, c, gs);
   a.fault[c] = sticky;
+  if (a.real_evap) a.evap_sum[c] = evap_sum;
 }
 
 __global__ void __launch_bounds__(128)

@@ -18,6 +18,7 @@ from .state import H9State
 
 MATH_EXACT = 0
 MATH_FAST = 1
+OPT_REAL_EVAP = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -57,6 +58,7 @@ ABI = {
     "h9_last_error": (C.c_char_p, [C.c_void_p]),
     "h9_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f, C.c_int]),
     "h9_set_math": (C.c_int, [C.c_void_p, C.c_int]),
+    "h9_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "h9_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "h9_set_soil": (C.c_int, [C.c_void_p, c_i, c_f, c_f, c_f, c_f, c_f]),
     "h9_num_land": (C.c_int64, [C.c_void_p]),
@@ -192,6 +194,9 @@ class H9:
 
     def set_math(self, mode: int):
         self._ck(self.lib.h9_set_math(self.h, mode), "h9_set_math")
+
+    def set_option(self, option: int, value: int):
+        self._ck(self.lib.h9_set_option(self.h, option, value), "h9_set_option")
 
     def set_tuning(self, tile_days: int = 0, block: int = 0):
         self._ck(self.lib.h9_set_tuning(self.h, tile_days, block), "h9_set_tuning")

@@ -84,6 +84,12 @@ int h9_configure(h9_ctx* ctx, int lon_c, int lat_c, int nisurf, const float zi[1
 /* H9_MATH_EXACT or H9_MATH_FAST; may be switched between runs. */
 int h9_set_math(h9_ctx* ctx, int mode);
 
+/* Options.  H9_OPT_REAL_EVAP (default 0): the reference never accumulates evap_sum
+ * (HYBRID9.f90:137,276), so axy_evap is identically 0 on land; 0 reproduces that, 1 makes
+ * h9_get_annual return the annual mean of qflx_evap_grnd + qflx_tran_veg_col (mm/s) instead. */
+#define H9_OPT_REAL_EVAP 1
+int h9_set_option(h9_ctx* ctx, int option, int value);
+
 /* Tuning knobs with no effect on results: days of forcing per pipeline tile of
  * h9_run_days (default 8, env H9_TILE_DAYS) and the launch shape of the
  * time-stepping kernel: threads per block (32, 64 or 128), plus 1000 to select the

@@ -705,7 +705,8 @@ struct h9o_ctx {
   int lon_c = 0, lat_c = 0, nisurf = 48, nyr = 1;
   Geometry geo;
   bool configured = false, have_soil = false;
-  int loop_order = 0, smp_leak = 0, nthreads = 1;
+  int loop_order = 0, smp_leak = 0, nthreads = 1, real_evap = 0;
+  std::vector<real> evap_sum;
   size_t ncell = 0;
   std::vector<int32_t> soil_tex, nplants, land;
   std::vector<real> theta_s, hksat, bsw, psi_s, fmax;
@@ -771,6 +772,7 @@ void cell_day(h9o_ctx* ctx, size_t ci, const Forcing& f, int iy, int day_abs) {
     ctx->npp_sum[ci] = zero;
     ctx->plant_mass_sum[ci] = zero;
     ctx->rnf_sum[ci] = zero;
+    ctx->evap_sum[ci] = zero;
     ctx->h2osoi_sum_total[ci] = zero;
     for (int I = 0; I < 8; ++I) ctx->theta_sum[8 * ci + I] = zero;
   }
@@ -779,6 +781,7 @@ void cell_day(h9o_ctx* ctx, size_t ci, const Forcing& f, int iy, int day_abs) {
   for (int NS = 1; NS <= ctx->nisurf; ++NS) { /* :193-211 */
     hydrology(ctx->geo, c, f, wx, &d);
     note_fault(ctx, ci, d.fault, day_abs, NS, d.w1 - d.w0);
+    if (ctx->real_evap) ctx->evap_sum[ci] = ctx->evap_sum[ci] + (d.qflx_evap_grnd + d.qflx_tran_veg_col);
   }
   GrowDiag gd;
   grow(ctx->geo, c, f.tas, &gd); /* :217 */
@@ -799,7 +802,8 @@ void cell_day(h9o_ctx* ctx, size_t ci, const Forcing& f, int iy, int day_abs) {
     ctx->axy_npp[o] = ctx->npp_sum[ci];
     ctx->axy_plant_mass[o] = ctx->plant_mass_sum[ci] / (real)nt;
     ctx->axy_rnf[o] = ctx->rnf_sum[ci] / (real)(nt * ctx->nisurf);
-    ctx->axy_evap[o] = zero / (real)(nt * ctx->nisurf); /* evap_sum is never accumulated :137,276 */
+    /* evap_sum is never accumulated in the reference (:137,276): 0 unless real_evap is on */
+    ctx->axy_evap[o] = (ctx->real_evap ? ctx->evap_sum[ci] : zero) / (real)(nt * ctx->nisurf);
     for (int I = 0; I < 8; ++I)
       ctx->axy_theta[8 * o + I] = ctx->theta_sum[8 * ci + I] / (real)nt;
     ctx->axy_theta_total[o] = ctx->h2osoi_sum_total[ci] / (real)nt;
@@ -867,6 +871,7 @@ int h9o_configure(h9o_ctx* ctx, int lon_c, int lat_c, int nisurf, const h9o_real
   ctx->npp_sum.assign(n, zero);
   ctx->plant_mass_sum.assign(n, zero);
   ctx->rnf_sum.assign(n, zero);
+  ctx->evap_sum.assign(n, zero);
   ctx->h2osoi_sum_total.assign(n, zero);
   ctx->theta_sum.assign(8 * n, zero);
   ctx->nt.assign(n, 0);
@@ -1022,6 +1027,12 @@ int h9o_set_options(h9o_ctx* ctx, int loop_order, int smp_leak, int nthreads) {
   ctx->loop_order = loop_order;
   ctx->smp_leak = smp_leak;
   ctx->nthreads = nthreads < 1 ? 1 : nthreads;
+  return 0;
+}
+
+int h9o_set_real_evap(h9o_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->real_evap = on ? 1 : 0;
   return 0;
 }
 

@@ -77,6 +77,10 @@ int h9o_get_state(h9o_ctx* ctx, h9o_real* h2osoi_liq, h9o_real* zwt, h9o_real* w
  *             used by the CPU baseline; cells are independent). */
 int h9o_set_options(h9o_ctx* ctx, int loop_order, int smp_leak, int nthreads);
 
+/* 0 (default): axy_evap == 0 like the reference (evap_sum is never accumulated,
+ * HYBRID9.f90:137,276); 1: annual mean of qflx_evap_grnd + qflx_tran_veg_col (mm/s) */
+int h9o_set_real_evap(h9o_ctx* ctx, int on);
+
 int h9o_run_days(h9o_ctx* ctx, int ndays, const int32_t* year_index_of_day, const h9o_real* tas,
                  const h9o_real* rlds, const h9o_real* rsds, const h9o_real* huss,
                  const h9o_real* ps, const h9o_real* pr, const h9o_real* rhs);

@@ -59,6 +59,7 @@ def load(kind: str = "f32"):
         "h9o_set_state": (C.c_int, [vp] + [rp] * 10 + [ip, rp]),
         "h9o_get_state": (C.c_int, [vp] + [rp] * 10 + [ip, rp]),
         "h9o_set_options": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+        "h9o_set_real_evap": (C.c_int, [vp, C.c_int]),
         "h9o_run_days": (C.c_int, [vp, C.c_int, ip] + [rp] * 7),
         "h9o_get_annual": (C.c_int, [vp, C.c_int] + [rp] * 6),
         "h9o_get_fault": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), ip, ip, ip,
@@ -137,6 +138,9 @@ class Oracle:
 
     def set_options(self, loop_order=0, smp_leak=0, nthreads=1):
         assert self.lib.h9o_set_options(self.h, loop_order, smp_leak, nthreads) == 0
+
+    def set_real_evap(self, on):
+        assert self.lib.h9o_set_real_evap(self.h, 1 if on else 0) == 0
 
     def init_state(self):
         assert self.lib.h9o_init_state(self.h) == 0

@@ -455,3 +455,30 @@ def test_missing_lambda_cells_do_not_poison_neighbours():
         h.close()
     good = w.land & ~bad
     assert_state_equal(out[0], out[1], good)
+
+
+def test_real_evaporation_option(world, forcing30):
+    """H9_OPT_REAL_EVAP: by default axy_evap == 0 like the reference (evap_sum is never
+    accumulated, HYBRID9.f90:137,276); with the option it is the annual mean ET flux."""
+    from hybrid9_b200.host import OPT_REAL_EVAP
+    st_init, _ = states(world)
+    nd = 10
+    f = {k: np.ascontiguousarray(v[:nd]) for k, v in forcing30.items()}
+    yi = np.ones(nd, np.int32)
+    o = make_oracle(world)
+    o.set_real_evap(True)
+    o.set_state(st_init)
+    o.run_days(yi, f)
+    ref = o.get_annual(1)["evap"]
+    land = world.land
+    assert (ref[land] > 0).mean() > 0.5
+    for mode, rtol in ((MATH_EXACT, 1e-4), (MATH_FAST, 5e-3)):
+        h = make_gpu(world, mode=mode)
+        h.set_option(OPT_REAL_EVAP, 1)
+        h.set_state(st_init)
+        assert h.run_days(yi, f) == 0
+        got = h.get_annual(1)["evap"]
+        err = np.abs(got[land].astype(np.float64) - ref[land]) - (1e-9 + rtol * np.abs(ref[land]))
+        assert (err <= 0).all(), (mode, err.max())
+        h.set_option(OPT_REAL_EVAP, 0)
+        h.close()
