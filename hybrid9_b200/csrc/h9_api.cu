@@ -942,6 +942,61 @@ int h9_grow_day(h9_ctx* ctx, const float* tas, float* npp, float* w_i, float* fT
   return H9_OK;
 }
 
+int h9_regrid_soil_layer(h9_ctx* ctx, int lon_c, int lat_c, int layer, const float* theta_s_in,
+                         const float* k_s_in, const float* lambda_in, const float* psi_s_in,
+                         float* theta_s, float* hksat, float* bsw, float* psi_s) {
+  if (!ctx) return H9_ERR_ARG;
+  if (lon_c < 1 || lat_c < 1 || layer < 1 || layer > NL || !theta_s_in || !k_s_in || !lambda_in ||
+      !psi_s_in || !theta_s || !hksat || !bsw || !psi_s)
+    return fail(ctx, H9_ERR_ARG, "h9_regrid_soil_layer: bad argument");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  const float* src[4] = {theta_s_in, k_s_in, lambda_in, psi_s_in};
+  float* dst[4] = {theta_s, hksat, bsw, psi_s};
+  const size_t fw = (size_t)lon_c * 60;
+  /* latitude bands of <= 64 MB per field on the device */
+  int band = (int)std::max<size_t>(1, (64u << 20) / (fw * 60 * sizeof(float)));
+  band = std::min(band, lat_c);
+  float *d_in = nullptr, *d_out = nullptr;
+  CK(cudaMalloc((void**)&d_in, 4 * (size_t)band * 60 * fw * sizeof(float)));
+  cudaError_t e = cudaMalloc((void**)&d_out, 4 * (size_t)band * lon_c * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(d_in);
+    return fail(ctx, H9_ERR_NOMEM, "h9_regrid_soil_layer: out of device memory");
+  }
+  std::vector<float> h((size_t)4 * band * lon_c);
+  int rc = H9_OK;
+  for (int y0 = 0; y0 < lat_c && rc == H9_OK; y0 += band) {
+    const int rows = std::min(band, lat_c - y0);
+    const size_t n = (size_t)rows * 60 * fw;
+    for (int f = 0; f < 4 && rc == H9_OK; ++f) {
+      if (cudaMemcpyAsync(d_in + f * n, src[f] + (size_t)y0 * 60 * fw, n * sizeof(float),
+                          cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = fail(ctx, H9_ERR_CUDA, "h9_regrid_soil_layer: H2D copy failed");
+      ctx->h2d += (int64_t)(n * sizeof(float));
+    }
+    if (rc != H9_OK) break;
+    if (launch_regrid_soil(ctx->stream, d_in, lon_c, rows, d_out) != 0) {
+      rc = fail(ctx, H9_ERR_CUDA, "h9_regrid_soil_layer: launch failed");
+      break;
+    }
+    ctx->launches += 1;
+    if (cudaMemcpyAsync(h.data(), d_out, (size_t)4 * rows * lon_c * sizeof(float), cudaMemcpyDeviceToHost,
+                        ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      rc = fail(ctx, H9_ERR_CUDA, std::string("h9_regrid_soil_layer: ") + cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    ctx->d2h += (int64_t)((size_t)4 * rows * lon_c * sizeof(float));
+    for (int f = 0; f < 4; ++f)
+      for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < lon_c; ++x)
+          dst[f][((size_t)(y0 + y) * lon_c + x) * NL + (layer - 1)] = h[((size_t)f * rows + y) * lon_c + x];
+  }
+  cudaFree(d_in);
+  cudaFree(d_out);
+  return rc;
+}
+
 int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const float* theta_s,
                            int nranks, int32_t* lat_s, int32_t* lat_count, int64_t* n_land) {
   if (lon_c < 1 || lat_c < 1 || !soil_tex || !theta_s || nranks < 1 || !lat_s || !lat_count)

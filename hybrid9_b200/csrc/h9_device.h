@@ -91,6 +91,9 @@ int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes] 
                         int ndays, size_t ngrid, const int32_t* d_cell_xy, int nc, int ncs,
                         float* d_out /* [ndays][7][ncs] */);
 int launch_clear_u32(void* stream, uint32_t* p, size_t n, uint32_t v);
+/* N4: 60x60 block means of the four 30-arc-second soil fields for `rows` coarse rows */
+int launch_regrid_soil(void* stream, const float* d_in /* [4][rows*60][lon_c*60] */, int lon_c, int rows,
+                       float* d_out /* [4][rows][lon_c]: theta_s, hksat, bsw, psi_s */);
 
 } /* namespace h9 */
 #endif

@@ -46,6 +46,50 @@ int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes],
   return (int)cudaGetLastError();
 }
 
+/* N4: INIT.f90:573-633.  One block per half-degree cell: the 60x60 fine cells of the four
+ * fields are brought into shared memory with coalesced loads, then four threads (one per
+ * field) add them up in the reference's order (x1 outer, y1 inner, only where theta_s_in >= 0)
+ * so that the float sums are bit-identical to the Fortran loop. */
+__global__ void __launch_bounds__(256)
+regrid_soil_kernel(const float* __restrict__ in, int lon_c, int rows, float* __restrict__ out) {
+  extern __shared__ float tile_raw[];
+  float (*tile)[60 * 61] = reinterpret_cast<float (*)[60 * 61]>(tile_raw); /* [field][y1][x1], padded rows */
+  const int x = blockIdx.x, y = blockIdx.y;
+  const size_t fw = (size_t)lon_c * 60, plane = fw * (size_t)rows * 60;
+  for (int k = threadIdx.x; k < 4 * 3600; k += blockDim.x) {
+    const int f = k / 3600, r = k % 3600, y1 = r / 60, x1 = r % 60;
+    tile[f][y1 * 61 + x1] = in[f * plane + ((size_t)y * 60 + y1) * fw + (size_t)x * 60 + x1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int f = threadIdx.x;
+    float sum = 0.0f;
+    int j = 0;
+    for (int x1 = 0; x1 < 60; ++x1)
+      for (int y1 = 0; y1 < 60; ++y1)
+        if (tile[0][y1 * 61 + x1] >= 0.0f) { /* :584 the mask is theta_s_in for all four */
+          sum = sum + tile[f][y1 * 61 + x1];
+          ++j;
+        }
+    if (j > 0) sum = sum / (float)j; /* :593-598 */
+    float v;
+    if (f == 0) v = sum / 1.0E3f;               /* theta_s :613 */
+    else if (f == 1) v = 10.0f * sum / 86400.0f; /* hksat   :614 */
+    else if (f == 2) v = 1.0f / fmaxf(sum / 1.0E3f, 1.0E-8f); /* lambda :615,624 -> bsw :628 */
+    else v = 10.0f * sum;                        /* psi_s   :616 */
+    out[((size_t)f * rows + y) * lon_c + x] = v;
+  }
+}
+
+int launch_regrid_soil(void* stream, const float* d_in, int lon_c, int rows, float* d_out) {
+  if (lon_c <= 0 || rows <= 0) return 0;
+  const size_t shm = 4 * 60 * 61 * sizeof(float); /* 58.6 KB: above the 48 KB static limit */
+  cudaError_t e = cudaFuncSetAttribute(regrid_soil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+  if (e != cudaSuccess) return (int)e;
+  regrid_soil_kernel<<<dim3(lon_c, rows), 256, shm, (cudaStream_t)stream>>>(d_in, lon_c, rows, d_out);
+  return (int)cudaGetLastError();
+}
+
 __global__ void clear_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

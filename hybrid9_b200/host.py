@@ -85,6 +85,7 @@ ABI = {
     "h9_reset_counters": (C.c_int, [C.c_void_p]),
     "h9_hydrology_step": (C.c_int, [C.c_void_p] + [c_f] * 7 + [c_f] * 5 + [c_i]),
     "h9_grow_day": (C.c_int, [C.c_void_p, c_f, c_f, c_f, c_f]),
+    "h9_regrid_soil_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [c_f] * 8),
     "h9_partition_lat_bands": (C.c_int, [C.c_int, C.c_int, c_i, c_f, C.c_int, c_i, c_i,
                                          C.POINTER(C.c_int64)]),
 }
@@ -301,6 +302,16 @@ class H9:
         self._ck(self.lib.h9_grow_day(self.h, _f(tas), _f(out["npp"]), _f(out["w_i"]),
                                       _f(out["fT"])), "h9_grow_day")
         return out
+
+    def regrid_soil_layer(self, lon_c, lat_c, layer, theta_s_in, k_s_in, lambda_in, psi_s_in,
+                          theta_s, hksat, bsw, psi_s):
+        """INIT.f90:573-633 for one layer: 30-arc-second fields (lat_c*60, lon_c*60) -> element
+        `layer` of the (lat_c, lon_c, 8) arrays."""
+        fine, coarse = (lat_c * 60, lon_c * 60), (lat_c, lon_c, 8)
+        ins = [_f(_chk32(a, fine, "fine field")) for a in (theta_s_in, k_s_in, lambda_in, psi_s_in)]
+        outs = [_f(_chk32(a, coarse, "soil array")) for a in (theta_s, hksat, bsw, psi_s)]
+        self._ck(self.lib.h9_regrid_soil_layer(self.h, lon_c, lat_c, layer, *ins, *outs),
+                 "h9_regrid_soil_layer")
 
     # -- faults, sync, counters ---------------------------------------------------
     def get_fault(self) -> H9Fault:

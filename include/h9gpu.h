@@ -209,6 +209,17 @@ int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const fl
  * Optional outputs (lon_c,lat_c): npp, w_i, fT. */
 int h9_grow_day(h9_ctx* ctx, const float* tas, float* npp, float* w_i, float* fT);
 
+/* INIT's soil pre-processing for ONE layer (INIT.f90:573-633): the four BNU fields at 30
+ * arc-seconds, each (lon_c*60, lat_c*60) with x fastest, are block-averaged 60x60 to the
+ * half-degree block over the cells whose theta_s_in >= 0 (sums in the reference's order:
+ * x1 outer, y1 inner; bit-exact), then converted: theta_s = mean/1e3, hksat = 10*mean/86400,
+ * lambda = max(mean/1e3, 1e-8), bsw = 1/lambda, psi_s = 10*mean.  Results go to element
+ * `layer` (1..8) of the (8,lon_c,lat_c) arrays.  Host pointers, pageable or pinned; the
+ * fine grids are staged through the device in latitude bands.  Only needs h9_create. */
+int h9_regrid_soil_layer(h9_ctx* ctx, int lon_c, int lat_c, int layer, const float* theta_s_in,
+                         const float* k_s_in, const float* lambda_in, const float* psi_s_in,
+                         float* theta_s, float* hksat, float* bsw, float* psi_s);
+
 /* Balanced contiguous latitude bands for `nranks` ranks: rows are assigned so
  * that every band holds about the same number of land cells (the reference's
  * INIT.f90:271-283 uses equal-area squares instead).  lat_s[r] is 1-based,

@@ -1201,6 +1201,43 @@ int h9o_get_geometry(const h9o_ctx* ctx, h9o_real dz[10], h9o_real zc[10], h9o_r
   return 0;
 }
 
+int h9o_regrid_soil_layer(int lon_c, int lat_c, int layer, const h9o_real* theta_s_in,
+                          const h9o_real* k_s_in, const h9o_real* lambda_in, const h9o_real* psi_s_in,
+                          h9o_real* theta_s, h9o_real* hksat, h9o_real* bsw, h9o_real* psi_s) {
+  if (lon_c < 1 || lat_c < 1 || layer < 1 || layer > 8) return -1;
+  const size_t fw = (size_t)lon_c * 60;
+  for (int y = 1; y <= lat_c; ++y)
+    for (int x = 1; x <= lon_c; ++x) { /* INIT.f90:579-599 */
+      real ts = zero, ks = zero, lm = zero, ps = zero;
+      int j = 0;
+      for (int x1 = (x - 1) * 60 + 1; x1 <= (x - 1) * 60 + 60; ++x1)
+        for (int y1 = (y - 1) * 60 + 1; y1 <= (y - 1) * 60 + 60; ++y1) {
+          const size_t k = (size_t)(y1 - 1) * fw + (size_t)(x1 - 1);
+          if (theta_s_in[k] >= zero) {
+            ts = ts + theta_s_in[k];
+            ks = ks + k_s_in[k];
+            lm = lm + lambda_in[k];
+            ps = ps + psi_s_in[k];
+            j = j + 1;
+          }
+        }
+      if (j > 0) {
+        ts = ts / (real)j;
+        ks = ks / (real)j;
+        lm = lm / (real)j;
+        ps = ps / (real)j;
+      }
+      const size_t o = ((size_t)(y - 1) * lon_c + (x - 1)) * 8 + (layer - 1);
+      theta_s[o] = ts / K(1.0E3);           /* :613 */
+      hksat[o] = K(10.0) * ks / K(86400.0); /* :614 */
+      real lambda = lm / K(1.0E3);          /* :615 */
+      psi_s[o] = K(10.0) * ps;              /* :616 */
+      lambda = rmax(lambda, trunc_);        /* :624 */
+      bsw[o] = K(1.0) / lambda;             /* :628 */
+    }
+  return 0;
+}
+
 int h9o_time_boy(int year) { /* INIT.f90:844-859 */
   if (year < 1860 || year > 2300) return -1;
   int t = 1;

@@ -104,6 +104,11 @@ int h9o_grow_day(h9o_ctx* ctx, const h9o_real* tas, h9o_real* npp, h9o_real* w_i
 /* full per-cell diagnostics of the last h9o_hydrology_step for block cell (x,y), 1-based */
 int h9o_last_step_diag(h9o_ctx* ctx, int x, int y, h9o_step_diag* out);
 
+/* INIT.f90:573-633 for one layer (see h9_regrid_soil_layer in include/h9gpu.h) */
+int h9o_regrid_soil_layer(int lon_c, int lat_c, int layer, const h9o_real* theta_s_in,
+                          const h9o_real* k_s_in, const h9o_real* lambda_in, const h9o_real* psi_s_in,
+                          h9o_real* theta_s, h9o_real* hksat, h9o_real* bsw, h9o_real* psi_s);
+
 /* geometry as INIT.f90:214,252-257 computes it: dz[1..9], zc[1..9] (index 0 unused), dt */
 int h9o_get_geometry(const h9o_ctx* ctx, h9o_real dz[10], h9o_real zc[10], h9o_real* dt);
 

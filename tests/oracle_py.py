@@ -70,6 +70,7 @@ def load(kind: str = "f32"):
         "h9o_last_step_diag": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "h9o_get_geometry": (C.c_int, [vp, rp, rp, rp]),
         "h9o_time_boy": (C.c_int, [C.c_int]),
+        "h9o_regrid_soil_layer": (C.c_int, [C.c_int, C.c_int, C.c_int] + [rp] * 8),
     }
     for n, (res, args) in sig.items():
         fn = getattr(lib, n)
