@@ -20,7 +20,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
                  const int32_t* __restrict__ year_index, const ForcingView fv, int cur_year,
                  int nt, unsigned long long step0, int cells_per_block,
                  const int32_t* __restrict__ cell_index) {
-  extern __shared__ float smem[];
+  extern __shared__ float4 smem[];
   /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells */
   const int c = blockIdx.x * cells_per_block + threadIdx.x;
   if (threadIdx.x >= cells_per_block || c >= a.nc) return; /* no barriers below */
@@ -87,7 +87,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     GrowOut go;
     grow_day<MathFast>(g, tas, gs, go);
 #pragma unroll
-    for (int i = 0; i < NL; ++i) tbl.set(FR_ROOTR, i, gs.rootr[i]);
+    for (int i = 0; i < NL; ++i) tbl.set_rootr(i, gs.rootr[i]);
 
     /* daily accumulators HYBRID9.f90:242-253: read-modify-write in L2-resident global memory */
     float npp_sum = new_year ? 0.0f : a.npp_sum[c];
@@ -148,7 +148,7 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, con
                            unsigned long long step0, const StepDiagArrays diag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
-  float col[kFastFloatsPerCell];
+  float4 col[kFastFloatsPerCell / 4];
   const CellTable<1> tbl{col};
   Params p;
   State gs;

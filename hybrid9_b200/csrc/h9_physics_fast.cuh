@@ -27,53 +27,56 @@
 
 namespace h9 {
 
-/* rows of the per-cell constant table (each row has NL entries, one per layer) */
-enum FastRow { FR_PSI = 0, FR_INV_NPSI, FR_E1, FR_COEF3, FR_INV_THS, FR_THS, FR_BSW, FR_HKS,
-               FR_INV_THS_SUM, FR_ROOTR, FR_NROWS };
-constexpr int kFastScalars = 2; /* fmax, min(hksat(1:3)) */
-constexpr int kFastFloatsPerCell = FR_NROWS * NL + kFastScalars;
+/* The per-cell constant table: three float4 groups per soil layer, so that one 128-bit
+ * shared-memory load brings the four constants a section of the sub-step needs:
+ *   G0 = (psi_s, 1/(-psi_s), 1-1/bsw, psi_s*theta_s/(1-1/bsw)/dz)      equilibrium profile
+ *   G1 = (theta_s, 1/theta_s, bsw, hksat)                              both sections
+ *   G2 = (1/(theta_s(I)+theta_s(I+1)), rootr_col(I), scalar, -)         hk section, beta, sinks
+ * The .z of G2 holds the per-cell scalars: layer 1 -> Fmax, layer 2 -> MINVAL(hksat(1:3)). */
+constexpr int kFastGroups = 3;
+constexpr int kFastFloatsPerCell = kFastGroups * NL * 4;
 
-/* one thread's column of the table: element (row, layer) lives at
- * base[(row*NL + layer) * STRIDE]; STRIDE = threads per block when the table is in
- * shared memory (consecutive threads -> consecutive banks), 1 for a local array */
+/* one thread's column: group gi of layer i lives at base[(gi*NL + i) * STRIDE] (float4 units);
+ * STRIDE = threads per block when the table is in shared memory (consecutive threads ->
+ * consecutive 16-byte slots: conflict-free 128-bit accesses), 1 for a local array */
 template <int STRIDE>
 struct CellTable {
-  float* base;
-  __device__ __forceinline__ float get(int row, int i) const { return base[(row * NL + i) * STRIDE]; }
-  __device__ __forceinline__ void set(int row, int i, float v) const { base[(row * NL + i) * STRIDE] = v; }
-  __device__ __forceinline__ float psi(int i) const { return get(FR_PSI, i); }
-  __device__ __forceinline__ float inv_npsi(int i) const { return get(FR_INV_NPSI, i); }
-  __device__ __forceinline__ float e1(int i) const { return get(FR_E1, i); }
-  __device__ __forceinline__ float coef3(int i) const { return get(FR_COEF3, i); }
-  __device__ __forceinline__ float inv_ths(int i) const { return get(FR_INV_THS, i); }
-  __device__ __forceinline__ float ths(int i) const { return get(FR_THS, i); }
-  __device__ __forceinline__ float bsw(int i) const { return get(FR_BSW, i); }
-  __device__ __forceinline__ float hks(int i) const { return get(FR_HKS, i); }
-  __device__ __forceinline__ float inv_ths_sum(int i) const { return get(FR_INV_THS_SUM, i); }
-  __device__ __forceinline__ float rootr(int i) const { return get(FR_ROOTR, i); }
-  __device__ __forceinline__ float fmax() const { return base[(FR_NROWS * NL + 0) * STRIDE]; }
-  __device__ __forceinline__ float hksmin3() const { return base[(FR_NROWS * NL + 1) * STRIDE]; }
+  float4* base;
+  __device__ __forceinline__ float4 g0(int i) const { return base[(0 * NL + i) * STRIDE]; }
+  __device__ __forceinline__ float4 g1(int i) const { return base[(1 * NL + i) * STRIDE]; }
+  __device__ __forceinline__ float4 g2(int i) const { return base[(2 * NL + i) * STRIDE]; }
+  __device__ __forceinline__ float comp(int gi, int i, int k) const {
+    return reinterpret_cast<const float*>(&base[(gi * NL + i) * STRIDE])[k];
+  }
+  __device__ __forceinline__ float psi(int i) const { return comp(0, i, 0); }
+  __device__ __forceinline__ float inv_npsi(int i) const { return comp(0, i, 1); }
+  __device__ __forceinline__ float e1(int i) const { return comp(0, i, 2); }
+  __device__ __forceinline__ float coef3(int i) const { return comp(0, i, 3); }
+  __device__ __forceinline__ float ths(int i) const { return comp(1, i, 0); }
+  __device__ __forceinline__ float inv_ths(int i) const { return comp(1, i, 1); }
+  __device__ __forceinline__ float bsw(int i) const { return comp(1, i, 2); }
+  __device__ __forceinline__ float hks(int i) const { return comp(1, i, 3); }
+  __device__ __forceinline__ float inv_ths_sum(int i) const { return comp(2, i, 0); }
+  __device__ __forceinline__ float rootr(int i) const { return comp(2, i, 1); }
+  __device__ __forceinline__ void set_rootr(int i, float v) const {
+    reinterpret_cast<float*>(&base[(2 * NL + i) * STRIDE])[1] = v;
+  }
+  __device__ __forceinline__ float fmax() const { return comp(2, 0, 2); }
+  __device__ __forceinline__ float hksmin3() const { return comp(2, 1, 2); }
 
   /* fill from the cell's parameters (once per launch) */
   __device__ __forceinline__ void init(const Geo& g, const Params& p, const float (&rootr)[NL]) const {
+    const float hmin = fminf(fminf(p.hksat[0], p.hksat[1]), p.hksat[2]);
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
       const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
       const float psi = p.psi_s[i], ths = p.theta_s[i], b = p.bsw[i];
       const float e1 = 1.0f - 1.0f / b;
-      set(FR_PSI, i, psi);
-      set(FR_INV_NPSI, i, 1.0f / (-psi));
-      set(FR_E1, i, e1);
-      set(FR_COEF3, i, psi * ths / e1 / (g.zi[i + 1] - g.zi[i]));
-      set(FR_INV_THS, i, 1.0f / ths);
-      set(FR_THS, i, ths);
-      set(FR_BSW, i, b);
-      set(FR_HKS, i, p.hksat[i]);
-      set(FR_INV_THS_SUM, i, 1.0f / (ths + p.theta_s[ip]));
-      set(FR_ROOTR, i, rootr[i]);
+      base[(0 * NL + i) * STRIDE] = make_float4(psi, 1.0f / (-psi), e1, psi * ths / e1 / (g.zi[i + 1] - g.zi[i]));
+      base[(1 * NL + i) * STRIDE] = make_float4(ths, 1.0f / ths, b, p.hksat[i]);
+      base[(2 * NL + i) * STRIDE] = make_float4(1.0f / (ths + p.theta_s[ip]), rootr[i],
+                                                i == 0 ? p.fmax : (i == 1 ? hmin : 0.0f), 0.0f);
     }
-    base[(FR_NROWS * NL + 0) * STRIDE] = p.fmax;
-    base[(FR_NROWS * NL + 1) * STRIDE] = fminf(fminf(p.hksat[0], p.hksat[1]), p.hksat[2]);
   }
 };
 
@@ -217,14 +220,15 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const float zlo = g.zi[i], zhi = g.zi[i + 1];
-    const float ths = c.ths(i), psi = c.psi(i), inv_npsi = c.inv_npsi(i), e1 = c.e1(i);
+    const float4 A = c.g0(i), B = c.g1(i); /* two 128-bit shared-memory loads per layer */
+    const float psi = A.x, inv_npsi = A.y, e1 = A.z, ths = B.x;
     /* (-psi+zwtmm-z)/(-psi) evaluated as 1 + (zwtmm-z)/(-psi): same value, no cancellation */
     const float t0 = fast_pow(fmaxf(fmaf(zwtmm - zlo, inv_npsi, 1.0f), 1.0f), e1);
     const float ti = fast_pow(fmaxf(fmaf(zwtmm - zhi, inv_npsi, 1.0f), 1.0f), e1);
-    const float coefA = c.coef3(i) * (zhi - zlo); /* psi*ths/e1 */
+    const float coefA = A.w * (zhi - zlo); /* psi*ths/e1 */
     float vol = fmaf(coefA, ti - t0, ths * fmaxf(zhi - zwtmm, 0.0f)) * g.rdzl[i + 1];
     vol = fminf(ths, fmaxf(vol, 0.0f));
-    zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+    zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * B.y, 0.01f), -B.z));
   }
   { /* :576-590: vol_eq(9) = A/(zwtmm-zi(8)) * (1 - (1+u)**e1), u = (zwtmm-zi(8))/(-psi).
      * Evaluated for every cell and selected by `deep`: straight-line code schedules better
@@ -252,12 +256,13 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
-    const float b = c.bsw(i), its = c.inv_ths_sum(i);
+    const float4 B = c.g1(i);
+    const float b = B.z, its = c.inv_ths_sum(i);
     const float s1 = fminf(1.0f, (theta[i] + theta[ip]) * its);
-    const float s2 = c.hks(i) * fast_pow(s1, fmaf(2.0f, b, 2.0f));
+    const float s2 = B.w * fast_pow(s1, fmaf(2.0f, b, 2.0f));
     hk[i] = s1 * s2;
     dhkdw[i] = fmaf(2.0f, b, 3.0f) * s2 * its;
-    const float inv_ths = c.inv_ths(i);
+    const float inv_ths = B.y;
     const float s_node = fminf(1.0f, fmaxf(theta[i] * inv_ths, 0.01f));
     const float sm = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
     s.smp[i] = sm;
