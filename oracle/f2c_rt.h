@@ -76,8 +76,9 @@ struct FArr {
   T& operator()(I... idx) {
     static_assert(sizeof...(I) == R, "rank mismatch");
     const long ii[R] = {(long)idx...};
-    long off = 0;
-    for (int d = 0; d < R; ++d) {
+    check(0, ii[0]);
+    long off = ii[0] - lo[0]; /* the first dimension is contiguous (column-major) */
+    for (int d = 1; d < R; ++d) {
       check(d, ii[d]);
       off += (ii[d] - lo[d]) * stride[d];
     }

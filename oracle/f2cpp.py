@@ -697,6 +697,7 @@ class Unit:
         self.blocks = []     # stack of ('do', label) / ('if',)
         self.nstop = 0
         self.tmp = 0
+        self.sync = None     # name of the write-back macro of a whole-subroutine unit
 
     def emit(self, s):
         self.out.append("  " * self.ind + s)
@@ -825,6 +826,8 @@ class Unit:
             return
         if re.match(r"^stop\b", s):
             self.nstop += 1
+            if self.sync:
+                self.emit(f"{self.sync};")
             self.emit(f"f2c_stop({self.nstop}, {where.split(':')[1]});")
             return
         m = re.match(r"^exit(?:\s+([a-z_][a-z0-9_]*))?$", s)
@@ -1000,10 +1003,19 @@ def main(src_dir: str, out_path: str):
         decl_lines += [f"  /* ---- locals of SUBROUTINE {sname.upper()} ({fname}) ---- */"] + d
         ctor_lines += c
         u = Unit(sname, fname, sc, lines)
+        u.sync = f"F2C_SYNC_{sname}"
         body = u.translate()
         protos.append(f"  void {sname}();")
+        # -DF2C_LOCALS: the subroutine's scalar locals are automatic variables (as in Fortran, so
+        # the compiler may keep them in registers) and are written back to the members of the
+        # same name on exit and before STOP, for the harness's diagnostics.  Default: members.
+        scal = [v for v in sc.syms.values() if v.rank == 0 and v.param is None]
+        loc = "".join(f"  {CTYPE[v.typ]} {v.cname} = 0;\n" for v in scal)
+        wb = " ".join(f"this->{v.cname} = {v.cname};" for v in scal)
+        pre = (f"#ifdef F2C_LOCALS\n{loc}#define {u.sync} do {{ {wb} }} while (0)\n"
+               f"#else\n#define {u.sync} do {{ }} while (0)\n#endif\n")
         bodies.append(f"void H9Ref::{sname}() {{ /* {fname}, whole file, {u.nstop} STOP statements */\n"
-                      + "\n".join(body) + "\n}\n")
+                      + pre + "\n".join(body) + f"\n  {u.sync};\n}}\n#undef {u.sync}\n")
         manifest.append(f"{fname}: SUBROUTINE {sname.upper()}, {len(lines)} statements")
     # fragments
     for name, fname, a, b, scname in FRAGMENTS:

@@ -6,12 +6,17 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs use it, and there only as the checker / CPU baseline.
  *
- * PARITY UNPINNED by the reference's own tests: the reference ships no tests,
- * golden vectors or fixtures and cannot be compiled in
- * this image (no Fortran compiler, no MPI, no netCDF).  The restatement follows
- * the Fortran source text statement by statement; what pins it is listed in
- * DESIGN.md ("Oracle"): hand-derived known answers from the INIT formulas,
- * the in-code invariants, and an FP64 build of the same source.
+ * PINNING.  The reference ships no tests, golden vectors or fixtures
+ * and the image has no Fortran compiler, MPI or netCDF, so the reference program itself
+ * cannot be built.  What pins this restatement instead is the reference's OWN source text,
+ * compiled: oracle/f2cpp.py translates HYDROLOGY.f90, GROW.f90 and the relevant line ranges
+ * of INIT.f90 / HYBRID9.f90 statement for statement into C++ (oracle/_ref/, built from
+ * /root/reference where it lies, never copied) and tests/test_ref_vs_oracle.py holds this
+ * file to it BIT FOR BIT: geometry, calendar, initial state, land mask, single HYDROLOGY calls
+ * with the water table in every layer, GROW, multi-day runs with and without the smp leak, a
+ * whole 3652-day decade through the verbatim loop nest, and the STOP record.  Outputs of that
+ * build are committed as tests/golden/h9_ref_golden_v1.npz.  Still not covered: the libm of the
+ * compiler the reference was actually built with (ifort's SVML); DESIGN.md section 4.
  *
  * Build: see oracle/Makefile.  `real` is float by default (the reference is
  * default-kind REAL throughout) and double with -DH9O_DOUBLE (noise floor).

@@ -231,3 +231,42 @@ def make_ref(world, nisurf=48, nyr=1, kind="ref", per_cell_smp=True):
     r.configure(world.nx, world.ny, nisurf, synth.ZI_DRIVER, nyr=nyr)
     r.set_soil(world.soil_tex, world.theta_s, world.hksat, world.bsw, world.psi_s, world.fmax)
     return r
+
+
+class RefRanks:
+    """The reference's parallel mode on one host: `nranks` independent instances, each owning
+    its own block of land cells and its own module state, stepped concurrently (one thread
+    each; ctypes releases the GIL).  This is what MPI ranks are to PROGRAM H9 -- blocks never
+    exchange anything during time stepping (INIT.f90:271-296, HYBRID9.f90:120-295).  Used by
+    bench.py for the CPU baseline; `kind` "o3" is the -O3 build."""
+
+    def __init__(self, world, forcing, ncell, nisurf, nranks, kind="o3"):
+        from hybrid9_b200 import synth
+        self.ranks, self.forcing, self.cells = [], [], 0
+        nranks = max(1, min(nranks, ncell))
+        for t in range(nranks):
+            a, b = ncell * t // nranks, ncell * (t + 1) // nranks
+            cw = synth.compact_world(world, b - a, start=a)
+            r = make_ref(cw, nisurf=nisurf, nyr=1, kind=kind, per_cell_smp=False)
+            r.init_state()
+            self.ranks.append(r)
+            self.forcing.append(synth.compact_forcing(world, forcing, b - a, start=a))
+            self.cells += r.num_land
+
+    def run_days(self, ndays):
+        """every rank runs HYBRID9.f90:120-295 over the first `ndays` days; returns seconds"""
+        import threading
+        import time
+        yi = np.ones(ndays, np.int32)
+        fs = [{k: np.ascontiguousarray(v[:ndays]) for k, v in f.items()} for f in self.forcing]
+        th = [threading.Thread(target=r.run_days, args=(yi, f)) for r, f in zip(self.ranks, fs)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
