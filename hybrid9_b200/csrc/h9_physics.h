@@ -78,6 +78,8 @@ struct Geo {
   float rdzw[10]; /* 1/dzw(I) */
   float rdzl[10]; /* 1/(zi(I)-zi(I-1)) */
   float rden[10]; /* 1/(zc(I+1)-zc(I)), I = 1..7 */
+  float zhr[10];  /* zi(I)/(zi(I)-zi(I-1)): (zi(I)-zwtmm)/dz(I) == zhr(I) - zwtmm*rdzl(I) */
+  float kbeta[10]; /* 1 - zc(I)/150000: the beta term 1-(smp-zc)/(-150000) == smp/150000 + kbeta */
   float rdt;      /* 1/dt */
   float dt;
   float q10_lo, q10_hi; /* -10/dt, 10/dt, HYDROLOGY.f90:894-895 */
@@ -100,6 +102,8 @@ inline void geo_init(Geo& g, const float zi[10], int nisurf) {
     g.rdzw[I] = I >= 1 ? 1.0f / g.dzw[I] : 0.0f;
     g.rdzl[I] = I >= 1 ? 1.0f / g.dz[I] : 0.0f;
     g.rden[I] = (I >= 1 && I <= 8) ? 1.0f / (g.zc[I + 1] - g.zc[I]) : 0.0f;
+    g.zhr[I] = I >= 1 ? g.zi[I] / g.dz[I] : 0.0f;
+    g.kbeta[I] = 1.0f - g.zc[I] / 150000.0f; /* 1 + (smp - zc)/150000 == smp/150000 + kbeta */
   }
   g.rdt = 1.0f / g.dt;
   g.q10_lo = -10.0f / g.dt;

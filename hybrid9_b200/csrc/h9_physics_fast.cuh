@@ -27,14 +27,15 @@
 
 namespace h9 {
 
-/* The per-cell constant table: three float4 groups per soil layer, so that one 128-bit
- * shared-memory load brings the four constants a section of the sub-step needs:
+/* The per-cell constant table: 27 float4 per cell.  Three groups per soil layer, so that one
+ * 128-bit shared-memory load brings the four constants a section of the sub-step needs:
  *   G0 = (psi_s, 1/(-psi_s), 1-1/bsw, psi_s*theta_s/(1-1/bsw)/dz)      equilibrium profile
  *   G1 = (theta_s, 1/theta_s, bsw, hksat)                              both sections
- *   G2 = (1/(theta_s(I)+theta_s(I+1)), rootr_col(I), scalar, -)         hk section, beta, sinks
- * The .z of G2 holds the per-cell scalars: layer 1 -> Fmax, layer 2 -> MINVAL(hksat(1:3)). */
+ *   G2 = (its = 1/(theta_s(I)+theta_s(I+1)), psi_s, (2*bsw+3)*its, -bsw/theta_s)   hk section
+ * then S = (Fmax, MINVAL(hksat(1:3)), -, -) and rootr_col(1:4), rootr_col(5:8) (beta and the
+ * sinks read all eight: two loads). */
 constexpr int kFastGroups = 3;
-constexpr int kFastFloatsPerCell = kFastGroups * NL * 4;
+constexpr int kFastFloatsPerCell = (kFastGroups * NL + 3) * 4;
 
 /* one thread's column: group gi of layer i lives at base[(gi*NL + i) * STRIDE] (float4 units);
  * STRIDE = threads per block when the table is in shared memory (consecutive threads ->
@@ -57,12 +58,13 @@ struct CellTable {
   __device__ __forceinline__ float bsw(int i) const { return comp(1, i, 2); }
   __device__ __forceinline__ float hks(int i) const { return comp(1, i, 3); }
   __device__ __forceinline__ float inv_ths_sum(int i) const { return comp(2, i, 0); }
-  __device__ __forceinline__ float rootr(int i) const { return comp(2, i, 1); }
+  __device__ __forceinline__ float4 rootr4(int h) const { return base[(kFastGroups * NL + 1 + h) * STRIDE]; }
+  __device__ __forceinline__ float rootr(int i) const { return comp(kFastGroups, 1 + (i >> 2), i & 3); }
   __device__ __forceinline__ void set_rootr(int i, float v) const {
-    reinterpret_cast<float*>(&base[(2 * NL + i) * STRIDE])[1] = v;
+    reinterpret_cast<float*>(&base[(kFastGroups * NL + 1 + (i >> 2)) * STRIDE])[i & 3] = v;
   }
-  __device__ __forceinline__ float fmax() const { return comp(2, 0, 2); }
-  __device__ __forceinline__ float hksmin3() const { return comp(2, 1, 2); }
+  __device__ __forceinline__ float fmax() const { return comp(kFastGroups, 0, 0); }
+  __device__ __forceinline__ float hksmin3() const { return comp(kFastGroups, 0, 1); }
 
   /* fill from the cell's parameters (once per launch) */
   __device__ __forceinline__ void init(const Geo& g, const Params& p, const float (&rootr)[NL]) const {
@@ -74,9 +76,12 @@ struct CellTable {
       const float e1 = 1.0f - 1.0f / b;
       base[(0 * NL + i) * STRIDE] = make_float4(psi, 1.0f / (-psi), e1, psi * ths / e1 / (g.zi[i + 1] - g.zi[i]));
       base[(1 * NL + i) * STRIDE] = make_float4(ths, 1.0f / ths, b, p.hksat[i]);
-      base[(2 * NL + i) * STRIDE] = make_float4(1.0f / (ths + p.theta_s[ip]), rootr[i],
-                                                i == 0 ? p.fmax : (i == 1 ? hmin : 0.0f), 0.0f);
+      const float its = 1.0f / (ths + p.theta_s[ip]);
+      base[(2 * NL + i) * STRIDE] = make_float4(its, psi, (2.0f * b + 3.0f) * its, -b / ths);
     }
+    base[(kFastGroups * NL + 1) * STRIDE] = make_float4(rootr[0], rootr[1], rootr[2], rootr[3]);
+    base[(kFastGroups * NL + 2) * STRIDE] = make_float4(rootr[4], rootr[5], rootr[6], rootr[7]);
+    base[(kFastGroups * NL) * STRIDE] = make_float4(p.fmax, hmin, 0.0f, 0.0f);
   }
 };
 
@@ -136,7 +141,8 @@ __device__ __forceinline__ float fast_pow(float a, float b) { return MathFast::e
 /* specific yield of layer I (0-based i) at water-table depth zwtmm, :963-965 */
 template <class C>
 __device__ __forceinline__ float fast_specific_yield(const C& c, int i, float zwtmm) {
-  const float s_y = c.ths(i) * (1.0f - fast_pow(fmaf(zwtmm, c.inv_npsi(i), 1.0f), -MathFast::rcp(c.bsw(i))));
+  /* -1/bsw == (1 - 1/bsw) - 1, the table's e1 */
+  const float s_y = c.ths(i) * (1.0f - fast_pow(fmaf(zwtmm, c.inv_npsi(i), 1.0f), c.e1(i) - 1.0f));
   return fmaxf(s_y, 0.02f);
 }
 
@@ -163,9 +169,11 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   float bw[NL];
 #pragma unroll
   for (int i = 0; i < NL; ++i)
-    bw[i] = __saturatef(fmaf(s.smp[i] - g.zc[i + 1], 1.0f / 150000.0f, 1.0f));
-  const float beta = fmaf(c.rootr(0), bw[0], fmaf(c.rootr(1), bw[1], fmaf(c.rootr(2), bw[2], c.rootr(3) * bw[3]))) +
-                     fmaf(c.rootr(4), bw[4], fmaf(c.rootr(5), bw[5], fmaf(c.rootr(6), bw[6], c.rootr(7) * bw[7])));
+    bw[i] = __saturatef(fmaf(s.smp[i], 1.0f / 150000.0f, g.kbeta[i + 1]));
+  const float4 ra = c.rootr4(0), rb = c.rootr4(1);
+  const float rr[NL] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+  const float beta = fmaf(rr[0], bw[0], fmaf(rr[1], bw[1], fmaf(rr[2], bw[2], rr[3] * bw[3]))) +
+                     fmaf(rr[4], bw[4], fmaf(rr[5], bw[5], fmaf(rr[6], bw[6], rr[7] * bw[7])));
 
   /* rsc :283-295, rss :325-331 */
   float rsc = (d.canopy_on && beta > 0.0f) ? d.rsc_num * MathFast::rcp(d.rsc_den0 * beta) : 1.0E6f;
@@ -175,25 +183,37 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
                         : fmaf(d.litter1000, 1.0f - theta[0] * c.inv_ths(0), 10.0f);
 
   /* two-source Penman-Monteith :344-389 */
-  const float PMc = d.pmc_num * MathFast::rcp(fmaf(d.gamma, fmaf(rsc, d.inv_raa_rac, 1.0f), d.desatdT));
-  const float PMs = d.pms_num * MathFast::rcp(fmaf(d.gamma, fmaf(rss, d.inv_raa_ras, 1.0f), d.desatdT));
+  /* two reciprocals from one MUFU: 1/a = b/(a*b), 1/b = a/(a*b) (both denominators are
+   * positive and of order 1e-4 .. 1e2) */
+  const float dPMc = fmaf(d.gamma, fmaf(rsc, d.inv_raa_rac, 1.0f), d.desatdT);
+  const float dPMs = fmaf(d.gamma, fmaf(rss, d.inv_raa_ras, 1.0f), d.desatdT);
   const float Rs = fmaf(d.gamma, rss, d.dg_ras);
   const float Rc = fmaf(d.gamma, rsc, d.dg_rac);
   /* Cc = 1/(1+Rc*Ra/(Rs*(Rc+Ra))) and Cs = 1/(1+Rs*Ra/(Rc*(Rs+Ra))) over the common
    * denominator Rs*Rc + Rs*Ra + Rc*Ra */
   const float RsRc = Rs * Rc, RsRa = Rs * d.Ra, RcRa = Rc * d.Ra;
-  const float invD = MathFast::rcp(RsRc + RsRa + RcRa);
+  /* three reciprocals from one MUFU */
+  const float dD = RsRc + RsRa + RcRa;
+  const float pPM = dPMc * dPMs;
+  const float r3 = MathFast::rcp(pPM * dD);
+  const float invD = r3 * pPM;
+  const float rPM = r3 * dD;
+  const float PMc = d.pmc_num * (rPM * dPMs);
+  const float PMs = d.pms_num * (rPM * dPMc);
   const float LE = fmaf(RsRc + RsRa, PMc, (RsRc + RcRa) * PMs) * invD;
   const float VDD0 = fmaf(d.A - d.dg * LE, d.raa_inv_rhocp, d.VDD);
   const float rv = d.rhocp * VDD0;
-  const float LEc = fmaf(rv, d.inv_rac, d.lec_a) * MathFast::rcp(fmaf(d.gamma, fmaf(rsc, d.inv_rac, 1.0f), d.desatdT));
-  const float LEs = fmaf(rv, d.inv_ras, d.les_a) * MathFast::rcp(fmaf(d.gamma, fmaf(rss, d.inv_ras, 1.0f), d.desatdT));
+  const float dLEc = fmaf(d.gamma, fmaf(rsc, d.inv_rac, 1.0f), d.desatdT);
+  const float dLEs = fmaf(d.gamma, fmaf(rss, d.inv_ras, 1.0f), d.desatdT);
+  const float rLE = MathFast::rcp(dLEc * dLEs);
+  const float LEc = fmaf(rv, d.inv_rac, d.lec_a) * (rLE * dLEs);
+  const float LEs = fmaf(rv, d.inv_ras, d.les_a) * (rLE * dLEc);
   const float qflx_tran_veg_col = LEc * d.k_lamb;
   float qflx_evap_grnd = LEs * d.k_lamb;
 
   /* evaporation limit :396-400 */
   const float evap_max1 =
-      fmaxf(0.0f, fmaf(-qflx_tran_veg_col, c.rootr(0), g.dz[1] * (theta[0] - kWatmin) * rdt));
+      fmaxf(0.0f, fmaf(-qflx_tran_veg_col, rr[0], g.dz[1] * (theta[0] - kWatmin) * rdt));
   qflx_evap_grnd = fminf(evap_max1, qflx_evap_grnd);
 
   /* Infiltration :426-478 */
@@ -205,8 +225,11 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   /* SoilWater :492-508 */
   float zwtmm = 1000.0f * s.zwt;
-  int jwt = find_jwt(g, s.zwt);
-  const bool deep = (jwt == NL);
+  /* jwt == NL  <=>  zwt > zi(8)/1000 (the interfaces increase); the full search only runs for
+   * cells whose water table is inside the column */
+  const bool deep = !(s.zwt <= g.zim[NL]);
+  int jwt = NL;
+  if (!deep) jwt = find_jwt(g, s.zwt);
 
   /* equilibrium profile :517-590, branch-free.  With B0 = (-psi+zwtmm-zi(I-1))/(-psi) and
    * BI = (-psi+zwtmm-zi(I))/(-psi), the three cases of the reference are one formula:
@@ -225,8 +248,8 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     /* (-psi+zwtmm-z)/(-psi) evaluated as 1 + (zwtmm-z)/(-psi): same value, no cancellation */
     const float t0 = fast_pow(fmaxf(fmaf(zwtmm - zlo, inv_npsi, 1.0f), 1.0f), e1);
     const float ti = fast_pow(fmaxf(fmaf(zwtmm - zhi, inv_npsi, 1.0f), 1.0f), e1);
-    const float coefA = A.w * (zhi - zlo); /* psi*ths/e1 */
-    float vol = fmaf(coefA, ti - t0, ths * fmaxf(zhi - zwtmm, 0.0f)) * g.rdzl[i + 1];
+    /* [A*(ti-t0) + ths*max(zhi-zwtmm,0)]/dz with A/dz from the table and zhi/dz from Geo */
+    float vol = fmaf(A.w, ti - t0, ths * fmaxf(fmaf(-zwtmm, g.rdzl[i + 1], g.zhr[i + 1]), 0.0f));
     vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * B.y, 0.01f), -B.z));
   }
@@ -252,21 +275,28 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   }
 
   /* hk, dhkdw, smp, dsmpdw :598-639 */
-  float hk[NL], dhkdw[NL], dsmpdw[NL];
+  float hk[NL], dhkdw[NL], dsmpdw[NL], snode[NL];
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
-    const float4 B = c.g1(i);
-    const float b = B.z, its = c.inv_ths_sum(i);
-    const float s1 = fminf(1.0f, (theta[i] + theta[ip]) * its);
+    const float4 B = c.g1(i), G = c.g2(i);
+    const float b = B.z;
+    const float s1 = fminf(1.0f, (theta[i] + theta[ip]) * G.x);
     const float s2 = B.w * fast_pow(s1, fmaf(2.0f, b, 2.0f));
     hk[i] = s1 * s2;
-    dhkdw[i] = fmaf(2.0f, b, 3.0f) * s2 * its;
-    const float inv_ths = B.y;
-    const float s_node = fminf(1.0f, fmaxf(theta[i] * inv_ths, 0.01f));
-    const float sm = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
+    dhkdw[i] = G.z * s2; /* (2b+3)*s2/(ths(I)+ths(I+1)) */
+    const float s_node = fminf(1.0f, fmaxf(theta[i] * B.y, 0.01f));
+    const float sm = fmaxf(kSmpmin, G.y * fast_pow(s_node, -b));
     s.smp[i] = sm;
-    dsmpdw[i] = (-b * inv_ths) * sm * MathFast::rcp(s_node);
+    snode[i] = s_node;
+    dsmpdw[i] = G.w * sm; /* (-b/ths)*smp, still to be divided by s_node */
+  }
+  /* two reciprocals from one MUFU: 1/a = b/(a*b), 1/b = a/(a*b); s_node is in [0.01, 1] */
+#pragma unroll
+  for (int k = 0; k < NL; k += 2) {
+    const float r = MathFast::rcp(snode[k] * snode[k + 1]);
+    dsmpdw[k] *= r * snode[k + 1];
+    dsmpdw[k + 1] *= r * snode[k];
   }
 
   /* aquifer node :645-650 and its interface :737-753; inert when the table is in the column */
@@ -287,9 +317,13 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
       const float b = c.bsw(i), inv_ths = c.inv_ths(i);
       const float s_node = fminf(1.0f, fmaxf(0.5f * fmaf(theta[i], inv_ths, 1.0f), 0.01f));
       const float smp1 = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
-      const float dsmpdw1 = (-b * inv_ths) * smp1 * MathFast::rcp(s_node);
       const float zc9 = 0.5f * (zwtmm + g.zc[NL]);
-      const float rden = MathFast::rcp(zc9 - g.zc[NL]);
+      /* 1/s_node and 1/(zc(9)-zc(8)) from one MUFU; the second factor is > 0 exactly for the
+       * cells (deep) whose results are kept below */
+      const float den9 = zc9 - g.zc[NL];
+      const float r9 = MathFast::rcp(s_node * den9);
+      const float rden = r9 * s_node;
+      const float dsmpdw1 = c.comp(2, i, 3) * smp1 * (r9 * den9);
       const float num = (smp1 - s.smp[i]) - (zq[NL] - zq[i]);
       const float nd = num * dhkdw[i];
       q[i] = deep ? -hk[i] * num * rden : 0.0f;
@@ -301,8 +335,10 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   /* tridiagonal rows :661-799 fused with the Thomas forward sweep :806-827 */
   float dwat2[NL + 1], gam[NL + 1];
   float bet, rbet, minpiv;
+  const float4 rc = c.rootr4(0), rd = c.rootr4(1); /* re-read: cheaper than eight live registers */
+  const float rs[NL] = {rc.x, rc.y, rc.z, rc.w, rd.x, rd.y, rd.z, rd.w};
   {
-    const float rmx = fmaf(-qflx_tran_veg_col, c.rootr(0), qflx_infl - q[0]);
+    const float rmx = fmaf(-qflx_tran_veg_col, rs[0], qflx_infl - q[0]);
     bet = g.dzdt[1] + qa[0];
     if (bet == 0.0f) fault |= FAULT_PIVOT1;
     rbet = MathFast::rcp(bet);
@@ -311,7 +347,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   }
 #pragma unroll
   for (int i = 1; i < NL; ++i) {
-    const float rmx = fmaf(-qflx_tran_veg_col, c.rootr(i), q[i - 1] - q[i]);
+    const float rmx = fmaf(-qflx_tran_veg_col, rs[i], q[i - 1] - q[i]);
     const float amx = -qa[i - 1];
     const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
     gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
@@ -420,8 +456,9 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
       s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* residual, unconditional :1100-1101 */
       s.wa += rsub_top_tot;
     }
-    jwt = find_jwt(g, s.zwt);
+    jwt = -1; /* :1110-1116, evaluated from zwt_j only where it is read (dryness repair, output) */
   }
+  const float zwt_j = s.zwt;
 
   s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
 
@@ -450,6 +487,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   for (int i = 1; i < NL; ++i) lowest = fminf(lowest, s.h2o[i]);
   float xs = 0.0f;
   if (lowest < kWatmin) {
+    if (jwt < 0) jwt = find_jwt(g, zwt_j);
 #pragma unroll
     for (int i = 0; i < NL - 1; ++i) {
       xs = fmaxf(kWatmin - s.h2o[i], 0.0f); /* > 0 exactly when h2o < watmin */
@@ -492,7 +530,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   o.qflx_evap_grnd = qflx_evap_grnd;
   o.rnf_inc = r1 + r2;
   o.imbalance = imb;
-  o.jwt = jwt;
+  o.jwt = (jwt < 0) ? find_jwt(g, zwt_j) : jwt; /* dead code where the caller ignores it (K3) */
   return fault;
 }
 
