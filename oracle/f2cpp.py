@@ -51,7 +51,9 @@ FRAGMENTS = [
     ("init_layers", "INIT.f90", 252, 263, "init"),         # dz, zc, zc_o
     ("init_alloc_grid_a", "INIT.f90", 301, 355, "init"),   # state, axy_*, soil_tex, Fmax ...
     ("init_alloc_grid_b", "INIT.f90", 374, 395, "init"),   # theta_s, hksat, lambda, bsw, psi_s
+    ("init_alloc_l1", "INIT.f90", 360, 370, "init"),       # 30 arc-second input tiles and their block means
     ("init_fills", "INIT.f90", 402, 414, "init"),          # NaN / zero fills of axy_*
+    ("init_regrid_layer", "INIT.f90", 575, 632, "init"),   # 60x60 block means -> layer I of the soil fields
     ("init_state", "INIT.f90", 711, 811, "init"),          # initial state of every land cell
     ("init_time_boy", "INIT.f90", 844, 859, "init"),       # calendar
     ("alloc_forcing", "INIT.f90", 901, 907, "init"),       # same shapes as READ_PGF.f90:33-108

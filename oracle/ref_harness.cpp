@@ -21,6 +21,7 @@
  *   h9r_run_decade       HYBRID9.f90:103-113 + :120-295 on the reference's own calendar
  *   h9r_hydrology_step   HYBRID9.f90:156-189 + one CALL HYDROLOGY for every land cell
  *   h9r_grow_day         one CALL GROW for every land cell
+ *   h9r_regrid_soil_layer INIT.f90:360-370 + :575-632, the 30 arc-second -> half-degree block means
  *
  * STOP (HYDROLOGY.f90:811,824,1071,1273) throws; the harness records which STOP, the cell,
  * the day and the sub-step, and returns the corresponding H9_FAULT_* bit.
@@ -478,6 +479,35 @@ int h9r_get_geometry(h9r_ctx* c, float dz[10], float zc[10], float* dt) {
 int h9r_time_boy(h9r_ctx* c, int year) {
   if (!c || !c->r || year < 1860 || year > 2300) return -1;
   return c->r->time_boy_(year - 1859);
+}
+
+/* INIT.f90:575-632 for one soil layer.  Inputs are the four
+ * 30-arc-second tiles (lon_c*60, lat_c*60) as NF90_GET_VAR leaves them (:541-568); outputs are
+ * (8,lon_c,lat_c) with only `layer` written, like h9o_regrid_soil_layer. */
+int h9r_regrid_soil_layer(int lon_c, int lat_c, int layer, const float* theta_s_in,
+                          const float* k_s_in, const float* lambda_in, const float* psi_s_in,
+                          float* theta_s, float* hksat, float* bsw, float* psi_s) {
+  if (lon_c < 1 || lat_c < 1 || layer < 1 || layer > 8) return -1;
+  H9Ref r;
+  r.lon_c_ = lon_c;
+  r.lat_c_ = lat_c;
+  r.init_alloc_l1();     /* INIT.f90:360-370 */
+  r.init_alloc_grid_b(); /* :374-395 */
+  copy_in(r.theta_s_l1_in_, theta_s_in);
+  copy_in(r.k_s_l1_in_, k_s_in);
+  copy_in(r.lambda_l1_in_, lambda_in);
+  copy_in(r.psi_s_l1_in_, psi_s_in);
+  r.i_ = layer; /* the DO I = 1, nsoil_layers_max of :475 */
+  r.init_regrid_layer();
+  for (int y = 1; y <= lat_c; ++y)
+    for (int x = 1; x <= lon_c; ++x) {
+      const size_t o = 8 * ((size_t)(y - 1) * lon_c + (x - 1)) + (layer - 1);
+      if (theta_s) theta_s[o] = r.theta_s_(layer, x, y);
+      if (hksat) hksat[o] = r.hksat_(layer, x, y);
+      if (bsw) bsw[o] = r.bsw_(layer, x, y);
+      if (psi_s) psi_s[o] = r.psi_s_(layer, x, y);
+    }
+  return 0;
 }
 
 int h9r_ndiag(void) { return H9R_NDIAG; }

@@ -68,6 +68,7 @@ def load(kind: str = "ref"):
         "h9r_get_fault": (C.c_int, [vp, C.POINTER(C.c_uint32), ip, ip, ip, ip, fp, ip]),
         "h9r_get_geometry": (C.c_int, [vp, fp, fp, fp]),
         "h9r_time_boy": (C.c_int, [vp, C.c_int]),
+        "h9r_regrid_soil_layer": (C.c_int, [C.c_int, C.c_int, C.c_int] + [fp] * 8),
         "h9r_ndiag": (C.c_int, []),
     }
     for n, (res, args) in sig.items():

@@ -47,6 +47,21 @@ def test_oracle_regrid_matches_a_float64_block_mean():
     assert np.all(ths[..., [0, 1, 3, 4, 5, 6, 7]] == 0)   # only the requested layer is written
 
 
+def test_oracle_regrid_equals_the_translated_reference():
+    """INIT.f90:575-632 as translated from the reference's own source (oracle/_ref): bit for bit."""
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref not built")
+    lib = ref_py.load()
+    fields = fine_fields()
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    for layer in (1, 4, 8):
+        got = [np.zeros((LAT_C, LON_C, 8), np.float32) for _ in range(4)]
+        assert lib.h9r_regrid_soil_layer(LON_C, LAT_C, layer, *[p(a) for a in fields], *[p(a) for a in got]) == 0
+        for a, b in zip(got, oracle_regrid(fields, layer)):
+            assert np.array_equal(a, b)
+
+
 @pytest.mark.gpu
 def test_gpu_regrid_is_bit_exact():
     fields = fine_fields()
