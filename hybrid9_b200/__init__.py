@@ -9,8 +9,10 @@ fails loudly when the CUDA library is missing.
 from .host import H9, H9Error, H9Fault, MATH_EXACT, MATH_FAST, load_library  # noqa: F401
 from .state import H9State, init_state  # noqa: F401
 from .calendar import time_boy, decade_days, year_index_of_days  # noqa: F401
+from .spinup import load_restart, save_restart, spin_up  # noqa: F401
 
 __all__ = [
     "H9", "H9Error", "H9Fault", "H9State", "init_state", "MATH_EXACT", "MATH_FAST",
-    "load_library", "time_boy", "decade_days", "year_index_of_days",
+    "load_library", "time_boy", "decade_days", "year_index_of_days", "save_restart",
+    "load_restart", "spin_up",
 ]

@@ -25,11 +25,10 @@ def test_restart_on_a_year_boundary_is_bit_exact(mode, tmp_path):
     b.set_state(init_state(w.soil_tex, w.theta_s, synth.ZI_DRIVER), with_smp=False)
     assert b.run_days(yi[:nd], {k: np.ascontiguousarray(v[:nd]) for k, v in f.items()}) == 0
     ck = b.get_state()
-    # the checkpoint survives a round trip through a flat file, like a restart file would
-    np.savez(tmp_path / "restart.npz", **{n: getattr(ck, n) for n in ck.names()})
-    z = np.load(tmp_path / "restart.npz")
-    for n in ck.names():
-        setattr(ck, n, np.ascontiguousarray(z[n]))
+    # the checkpoint goes through the flat restart file of hybrid9_b200/spinup.py
+    from hybrid9_b200 import load_restart, save_restart
+    save_restart(str(tmp_path / "restart.h9"), ck)
+    ck = load_restart(str(tmp_path / "restart.h9"))
     b.close()
     c = make_gpu(w, nyr=2, mode=mode)
     c.set_state(ck, with_smp=True)   # smp is part of the state
@@ -39,3 +38,18 @@ def test_restart_on_a_year_boundary_is_bit_exact(mode, tmp_path):
         assert np.array_equal(v, c.get_annual(2)[k], equal_nan=True), k
     a.close()
     c.close()
+
+
+def test_spin_up_controller_converges():
+    """N3: cycling one forcing year until the land-mean annual soil water drifts by < 0.5 mm per
+    cycle; the drift shrinks and the controller stops before its cycle limit."""
+    from hybrid9_b200 import spin_up
+    w = synth.make_world(nx=72, ny=36, seed=9)
+    f = synth.make_forcing(w, 365, seed=4)
+    h = make_gpu(w, nyr=1, mode=MATH_FAST)
+    h.set_state(init_state(w.soil_tex, w.theta_s, synth.ZI_DRIVER), with_smp=False)
+    hist = spin_up(h, np.ones(365, np.int32), f, w.land, max_cycles=60, tol_mm=0.5)
+    drifts = [d for _, _, d in hist[1:]]
+    assert len(hist) < 60 and drifts[-1] < 0.5
+    assert drifts[-1] < drifts[0]
+    h.close()
