@@ -35,7 +35,7 @@ from __future__ import annotations
 
 import re
 import sys
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 # ------------------------------------------------------------------------------------------
 # what to translate: (function name, file, first line, last line) -- 1-based, inclusive
@@ -486,8 +486,6 @@ def real_literal(text: str) -> str:
     t = text.replace("d", "e")
     if "." not in t and "e" not in t:
         t += ".0"
-    if re.match(r"^\d+e", t):  # 1e3 -> fine in C
-        pass
     return t + "f"
 
 
