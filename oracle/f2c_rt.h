@@ -12,6 +12,17 @@
  */
 #pragma once
 #include <cmath>
+#ifdef F2C_PORTABLE_MATH
+/* Build variant libh9ref_pk.so: EXP / LOG / real**real go to the portable, bit-reproducible
+ * double-precision kernels that the GPU's exact mode uses (hybrid9_b200/csrc/h9_physics.h,
+ * h9::MathExact) instead of glibc's.  With the same three functions on both sides, the GPU's
+ * exact mode must reproduce the translated reference BIT FOR BIT (tests/test_gpu_vs_ref_bitwise.py);
+ * only these functions are taken from that header, no physics. */
+#include "../hybrid9_b200/csrc/h9_physics.h"
+#define powf(a, b) h9::MathExact::pow((a), (b))
+#define expf(a) h9::MathExact::exp((a))
+#define logf(a) h9::MathExact::log((a))
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -22,7 +22,8 @@ FORCING = ("tas", "rlds", "rsds", "huss", "ps", "pr", "rhs")
 DIAG = ("qflx_surf", "rsub_top", "qflx_rsub_sat", "qflx_infl", "qcharge", "fsat", "beta", "rsc",
         "w0", "w1", "rous", "zwtmm", "desatdT", "gamma", "rho", "Rnets")
 _LIBS = {}
-_NAMES = {"ref": "libh9ref.so", "o3": "libh9ref_o3.so", "chk": "libh9ref_chk.so"}
+_NAMES = {"ref": "libh9ref.so", "o3": "libh9ref_o3.so", "chk": "libh9ref_chk.so",
+          "pk": "libh9ref_pk.so"}
 
 
 def build():
@@ -41,7 +42,8 @@ def available(kind: str = "ref") -> bool:
 
 
 def load(kind: str = "ref"):
-    """kind: ref (strict IEEE, the pin), o3 (CPU-baseline build), chk (bounds-checked)."""
+    """kind: ref (strict IEEE, the pin), o3 (CPU-baseline build), chk (bounds-checked), pk (ref with
+    the GPU exact mode's portable pow/exp/log instead of glibc's)."""
     if kind in _LIBS:
         return _LIBS[kind]
     if not available(kind):

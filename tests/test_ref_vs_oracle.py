@@ -253,3 +253,25 @@ def test_bounds_checked_build_runs_clean(world, forcing):
         assert r.run_days(np.ones(2, np.int32), f) == 0
         out.append(r.get_state())
     assert_state_equal(out[0], out[1], world.land, fields=ALL_FIELDS)
+
+
+@pytest.mark.parametrize("tag", ["init", "random"])
+def test_kernel_source_equals_the_translated_reference_under_the_same_math(world, forcing, tag):
+    """The GPU's exact-mode physics (hybrid9_b200/csrc/h9_physics.h compiled for the host,
+    tests/twin) against the translated reference built with the SAME portable pow/exp/log
+    (libh9ref_pk.so): bit for bit.  The GPU reproduces that host build bit for bit
+    (tests/test_gpu_parity.py) and is compared with libh9ref_pk.so directly in
+    tests/test_gpu_vs_ref_bitwise.py."""
+    if not ref_py.available("pk"):
+        pytest.skip("libh9ref_pk.so not present")
+    st0 = init_state(world.soil_tex, world.theta_s, synth.ZI_DRIVER)
+    if tag == "random":
+        st0 = synth.randomize_state(world, st0, seed=23)
+    nd = 8
+    f = {k: np.ascontiguousarray(v[:nd]) for k, v in forcing.items()}
+    r = ref_py.make_ref(world, kind="pk")
+    r.set_state(st0)
+    assert r.run_days(np.ones(nd, np.int32), f) == 0
+    tw, ex = oracle_py.twin_run(world, st0, f, 48, synth.ZI_DRIVER, math="exact")
+    assert not ex["fault"].any()
+    assert_state_equal(r.get_state(), tw, world.land)
