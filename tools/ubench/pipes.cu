@@ -37,6 +37,11 @@ __global__ void k(float* out, int iters, float b, float c) {
       if (MODE == 11) { OP_FMUL(a[i], b); OP_FADD(a[i], c); OP_FMNMX(a[i], c); OP_FFMA3(a[i], b, c);
                         OP_FMUL(a[i], b); OP_FADD(a[i], c); OP_FMNMX(a[i], c); OP_EX2(a[i]); }            // 7 : 1
       if (MODE == 12) { OP_FMUL(a[i], b); OP_FADD(a[i], c); OP_FMNMX(a[i], c); OP_EX2(a[i]); }            // 3 : 1
+      if (MODE == 13) { /* one pow per accumulator: clamp, lg2, *b, ex2, then 3 dependent FMA-pipe ops (6 : 2) */
+        OP_FMNMX(a[i], c); OP_FADD(a[i], b); OP_LG2(a[i]); OP_FMUL(a[i], b); OP_EX2(a[i]); OP_FMUL(a[i], b); OP_FADD(a[i], c); OP_FMUL(a[i], b); }
+      if (MODE == 14) { /* the same with 12 FMA/ALU ops per pow (12 : 2), the fast step's overall ratio is ~8.7 : 1 */
+        OP_FMNMX(a[i], c); OP_FADD(a[i], b); OP_LG2(a[i]); OP_FMUL(a[i], b); OP_EX2(a[i]); OP_FMUL(a[i], b); OP_FADD(a[i], c); OP_FMUL(a[i], b);
+        OP_FADD(a[i], c); OP_FMUL(a[i], b); OP_FMNMX(a[i], c); OP_FADD(a[i], c); OP_FMUL(a[i], b); OP_FADD(a[i], c); }
     }
   }
   float s = 0;
@@ -45,10 +50,10 @@ __global__ void k(float* out, int iters, float b, float c) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-static const int kOps[13] = {8, 8, 8, 8, 8, 8, 16, 16, 32, 57, 60, 64, 32};
-static const char* kName[13] = {"FFMA 3-reg", "FFMA imm", "FMUL", "FADD", "FMNMX", "MUFU.EX2", "FMUL+FADD",
+static const int kOps[15] = {8, 8, 8, 8, 8, 8, 16, 16, 32, 57, 60, 64, 32, 64, 112};
+static const char* kName[15] = {"FFMA 3-reg", "FFMA imm", "FMUL", "FADD", "FMNMX", "MUFU.EX2", "FMUL+FADD",
                                 "FMUL+FMNMX", "FMUL+FADD+FMNMX+FFMA", "mix 56 : 1 MUFU", "mix 56 : 4 MUFU",
-                                "mix 7 : 1 MUFU", "mix 3 : 1 MUFU"};
+                                "mix 7 : 1 MUFU", "mix 3 : 1 MUFU", "8 pows, 6 FMA : 2 MUFU", "8 pows, 12 FMA : 2 MUFU"};
 
 template <int MODE>
 void run(float* d, int nsm, double ghz) {
@@ -81,6 +86,6 @@ int main() {
   cudaMalloc(&d, sizeof(float) * nsm * 512);
   run<0>(d, nsm, ghz); run<1>(d, nsm, ghz); run<2>(d, nsm, ghz); run<3>(d, nsm, ghz); run<4>(d, nsm, ghz);
   run<5>(d, nsm, ghz); run<6>(d, nsm, ghz); run<7>(d, nsm, ghz); run<8>(d, nsm, ghz); run<9>(d, nsm, ghz);
-  run<10>(d, nsm, ghz); run<11>(d, nsm, ghz); run<12>(d, nsm, ghz);
+  run<10>(d, nsm, ghz); run<11>(d, nsm, ghz); run<12>(d, nsm, ghz); run<13>(d, nsm, ghz); run<14>(d, nsm, ghz);
   return 0;
 }
