@@ -332,6 +332,29 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     }
   }
 
+  /* Parts of Recharge/Drainage (:856-965) that do not depend on the solve are issued before
+   * it, so that their pow chains run behind the Thomas sweep instead of after it: the aquifer's
+   * specific yield, and for a water table inside the column the Darcy recharge and the
+   * specific yield of the layer that holds the table. */
+  const float rous_early = fast_specific_yield(c, NL - 1, zwtmm);
+  const float rrous_early = MathFast::rcp(rous_early);
+  float qcharge_early = 0.0f, sy_first = 0.02f;
+  if (!deep) {
+    const int jm = (jwt > 1 ? jwt : 1) - 1;
+    const float th_j = pick<NL>(theta, jwt);
+    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
+    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
+    const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
+    float zq_j = zq[0];
+#pragma unroll
+    for (int k = 1; k < NL; ++k)
+      if (jm == k) zq_j = zq[k];
+    const float wh = smp1 - zq_j;
+    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    qcharge_early = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
+    qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
+    sy_first = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
+  }
   /* tridiagonal rows :661-799 fused with the Thomas forward sweep :806-827 */
   float dwat2[NL + 1], gam[NL + 1];
   float bet, rbet, minpiv;
@@ -375,35 +398,19 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   /* recharge :856-904 */
   float qcharge;
-  if (!deep) {
-    const int jm = (jwt > 1 ? jwt : 1) - 1;
-    const float th_j = pick<NL>(theta, jwt);
-    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
-    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
-    const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
-    float zq_j = zq[0];
-#pragma unroll
-    for (int k = 1; k < NL; ++k)
-      if (jm == k) zq_j = zq[k];
-    const float wh = smp1 - zq_j;
-    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
-    qcharge = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
-    qcharge = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge));
-  } else {
-    qcharge = dwat2[NL] * dz9 * rdt;
-  }
-
+  qcharge = deep ? dwat2[NL] * dz9 * rdt : qcharge_early;
   /* Drainage :923-1009.  The jwt of :923-931 equals the one of :499-508: zwt has not
    * changed in between */
-  float rous = fast_specific_yield(c, NL - 1, zwtmm);
+  float rous = rous_early;
+  const int jfirst = jwt + 1;
   if (jwt == NL) {
     s.wa = fmaf(qcharge, dt, s.wa);
-    s.zwt = fmaf(-(qcharge * dt * 0.001f), MathFast::rcp(rous), s.zwt);
+    s.zwt = fmaf(-(qcharge * dt * 0.001f), rrous_early, s.zwt);
   } else { /* zwtmm stays the stale value of :492 inside the loops */
     float qcharge_tot = qcharge * dt;
     if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
       for (int I = jwt + 1; I >= 1; --I) {
-        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+        const float s_y = (I == jfirst) ? sy_first : fast_specific_yield(c, I - 1, zwtmm);
         const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
         s.zwt -= ql * MathFast::rcp(s_y) * 0.001f; /* s_y >= 0.02 > 0 */
         qcharge_tot -= ql;
@@ -411,7 +418,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
       }
     } else { /* deepening, layers jwt+1 .. 8 */
       for (int I = jwt + 1; I <= NL; ++I) {
-        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+        const float s_y = (I == jfirst) ? sy_first : fast_specific_yield(c, I - 1, zwtmm);
         const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
         qcharge_tot -= ql;
         if (qcharge_tot >= 0.0f) {
@@ -420,7 +427,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
         }
         s.zwt = g.zim[I];
       }
-      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * MathFast::rcp(rous);
+      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
     }
     jwt = find_jwt(g, s.zwt);
   }
@@ -445,7 +452,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
         const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
 #pragma unroll
         for (int k = 0; k < NL; ++k)
-          if (k == I - 1) s.h2o[k] += rl;
+          s.h2o[k] = (k == I - 1) ? s.h2o[k] + rl : s.h2o[k]; /* a select, not a jump table */
         rsub_top_tot -= rl;
         if (rsub_top_tot >= 0.0f) {
           s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
