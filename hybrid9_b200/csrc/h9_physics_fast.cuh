@@ -469,12 +469,21 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
 
   s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
 
-  /* excess cascade :1131-1152: a no-op unless some layer is above its capacity */
+  /* excess cascade :1131-1152 and dryness repair :1161-1205: both are no-ops unless some layer
+   * is above its capacity / below watmin, so ONE rarely taken branch guards them.  The repair's
+   * trigger is taken before the cascade: the cascade only lowers layers to their capacity
+   * (>= 0.01*dz > watmin) and raises others, so it cannot create a layer below watmin, and
+   * inside the branch the repair works from the current values anyway. */
   float over = s.h2o[0] - fmaxf(0.0f, c.ths(0) * g.dz[1]);
+  float lowest = s.h2o[0];
 #pragma unroll
-  for (int i = 1; i < NL; ++i) over = fmaxf(over, fmaf(-fmaxf(0.01f, c.ths(i)), g.dz[i + 1], s.h2o[i]));
+  for (int i = 1; i < NL; ++i) {
+    over = fmaxf(over, fmaf(-fmaxf(0.01f, c.ths(i)), g.dz[i + 1], s.h2o[i]));
+    lowest = fminf(lowest, s.h2o[i]);
+  }
   float qflx_rsub_sat = 0.0f;
-  if (over > 0.0f) {
+  float xs = 0.0f;
+  if (over > 0.0f || lowest < kWatmin) {
 #pragma unroll
     for (int i = NL - 1; i >= 1; --i) {
       const float cap = fmaxf(0.01f, c.ths(i)) * g.dz[i + 1];
@@ -486,14 +495,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     const float xs1 = fmaxf(fmaxf(s.h2o[0], 0.0f) - cap1, 0.0f);
     s.h2o[0] = fminf(cap1, s.h2o[0]);
     qflx_rsub_sat = xs1 * rdt;
-  }
 
-  /* dryness repair :1161-1205: a no-op unless some layer is below watmin */
-  float lowest = s.h2o[0];
-#pragma unroll
-  for (int i = 1; i < NL; ++i) lowest = fminf(lowest, s.h2o[i]);
-  float xs = 0.0f;
-  if (lowest < kWatmin) {
     if (jwt < 0) jwt = find_jwt(g, zwt_j);
 #pragma unroll
     for (int i = 0; i < NL - 1; ++i) {
