@@ -16,7 +16,11 @@
  *     denominator; interface fluxes are computed once per interface (the
  *     reference writes each twice, as qout(I) and qin(I+1));
  *   - the data-dependent Drainage loops are real loops over the shared-memory
- *     constants instead of 8-fold predicated unrolls (code size, I-cache).
+ *     constants instead of 8-fold predicated unrolls (code size, I-cache);
+ *   - latency: layers are processed in pairs, each pair followed at once by the interface
+ *     fluxes and the Thomas rows it completes (the sweep's reciprocal chain runs behind the
+ *     powers of the deeper layers), and the parts of Recharge/Drainage that do not depend on
+ *     the solve are issued before it.
  * Results differ from the exact mode at rounding level only; the deviation is
  * measured against the oracle and the FP32 noise floor in tests/test_gpu_parity.py.
  */
@@ -237,47 +241,35 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
    * below the layer both bases are >= 1 and the last term vanishes (:548-558); inside it
    * BI < 1 so the first power is tempi = 1 (:532-540); above it both powers are 1 and
    * (zi(I)-zwtmm)/dz >= 1 so the clamp to theta_s returns theta_s (:523). */
+  /* Layers are processed in pairs and each pair is followed at once by the interface fluxes it
+   * completes and by the rows of the Thomas forward sweep those fluxes complete: the sweep's
+   * dependent chain (one reciprocal per row) then runs behind the powers of the deeper layers
+   * instead of after all of them.  Same operations on the same operands as the separate
+   * loops: the results are bit-identical. */
   float zq[NL + 1];
-  /* (a variant specialised for the all-layers-below case was slower: warps that mix deep and
-   * shallow cells then execute both loops) */
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
+  float hk[NL], dhkdw[NL], dsmpdw[NL], snode[NL];
+  float q[NL], qa[NL], qb[NL]; /* per interface i (below layer i): flux and its two derivatives */
+  float dwat2[NL + 1], gam[NL + 1];
+  float bet = 1.0f, rbet = 1.0f, minpiv = 3.0e38f;
+  const float dz9 = deep ? (zwtmm - g.zc[NL]) : g.dz[NL];
+  const float4 rc = c.rootr4(0), rd = c.rootr4(1); /* re-read: cheaper than eight live registers */
+  const float rs[NL] = {rc.x, rc.y, rc.z, rc.w, rd.x, rd.y, rd.z, rd.w};
+  /* parts of Recharge/Drainage (:856-965) that do not depend on the solve: the aquifer's
+   * specific yield and its reciprocal */
+  const float rous_early = fast_specific_yield(c, NL - 1, zwtmm);
+  const float rrous_early = MathFast::rcp(rous_early);
+
+  auto eq_layer = [&](int i) { /* equilibrium profile :517-573 of layer i+1 */
     const float zlo = g.zi[i], zhi = g.zi[i + 1];
     const float4 A = c.g0(i), B = c.g1(i); /* two 128-bit shared-memory loads per layer */
     const float psi = A.x, inv_npsi = A.y, e1 = A.z, ths = B.x;
-    /* (-psi+zwtmm-z)/(-psi) evaluated as 1 + (zwtmm-z)/(-psi): same value, no cancellation */
     const float t0 = fast_pow(fmaxf(fmaf(zwtmm - zlo, inv_npsi, 1.0f), 1.0f), e1);
     const float ti = fast_pow(fmaxf(fmaf(zwtmm - zhi, inv_npsi, 1.0f), 1.0f), e1);
-    /* [A*(ti-t0) + ths*max(zhi-zwtmm,0)]/dz with A/dz from the table and zhi/dz from Geo */
     float vol = fmaf(A.w, ti - t0, ths * fmaxf(fmaf(-zwtmm, g.rdzl[i + 1], g.zhr[i + 1]), 0.0f));
     vol = fminf(ths, fmaxf(vol, 0.0f));
     zq[i] = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * B.y, 0.01f), -B.z));
-  }
-  { /* :576-590: vol_eq(9) = A/(zwtmm-zi(8)) * (1 - (1+u)**e1), u = (zwtmm-zi(8))/(-psi).
-     * Evaluated for every cell and selected by `deep`: straight-line code schedules better
-     * than a divergent region, and most cells are deep */
-    const int i = NL - 1;
-    const float ths = c.ths(i), psi = c.psi(i), e1 = c.e1(i), inv_npsi = c.inv_npsi(i);
-    const float u = (zwtmm - g.zi[NL]) * inv_npsi;
-    /* r = ((1+u)**e1 - 1)/u.  The direct form loses every digit as the water table nears the
-     * column base (u -> 0, where the reference's own float evaluation is noise); the
-     * binomial series keeps r accurate there. */
-    const float a2 = 0.5f * (e1 - 1.0f), a3 = (1.0f / 3.0f) * (e1 - 2.0f), a4 = 0.25f * (e1 - 3.0f);
-    const float r_series = e1 * fmaf(u * a2, fmaf(u * a3, fmaf(u, a4, 1.0f), 1.0f), 1.0f);
-    const float r_direct = (fast_pow(1.0f + u, e1) - 1.0f) * MathFast::rcp(u);
-    const float r = (u < 0.03f) ? r_series : r_direct;
-    /* A/(zwtmm-zi(8)) * (1-temp0) = -A * inv_npsi * r */
-    const float coefA = c.coef3(i) * (g.zi[NL] - g.zi[NL - 1]);
-    float vol = -coefA * inv_npsi * r;
-    vol = fminf(ths, fmaxf(vol, 0.0f));
-    const float z9 = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
-    zq[NL] = deep ? z9 : 0.0f;
-  }
-
-  /* hk, dhkdw, smp, dsmpdw :598-639 */
-  float hk[NL], dhkdw[NL], dsmpdw[NL], snode[NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
+  };
+  auto hk_layer = [&](int i) { /* hk, dhkdw, smp, dsmpdw :598-639 of layer i+1 */
     const int ip = (i + 1 < NL) ? i + 1 : NL - 1;
     const float4 B = c.g1(i), G = c.g2(i);
     const float b = B.z;
@@ -290,54 +282,97 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     s.smp[i] = sm;
     snode[i] = s_node;
     dsmpdw[i] = G.w * sm; /* (-b/ths)*smp, still to be divided by s_node */
-  }
-  /* two reciprocals from one MUFU: 1/a = b/(a*b), 1/b = a/(a*b); s_node is in [0.01, 1] */
-#pragma unroll
-  for (int k = 0; k < NL; k += 2) {
+  };
+  auto pair_rcp = [&](int k) { /* two reciprocals from one MUFU; s_node is in [0.01, 1] */
     const float r = MathFast::rcp(snode[k] * snode[k + 1]);
     dsmpdw[k] *= r * snode[k + 1];
     dsmpdw[k + 1] *= r * snode[k];
-  }
-
-  /* aquifer node :645-650 and its interface :737-753; inert when the table is in the column */
-  const float dz9 = deep ? (zwtmm - g.zc[NL]) : g.dz[NL];
-  float q[NL], qa[NL], qb[NL]; /* per interface i (below layer i): flux and its two derivatives */
-#pragma unroll
-  for (int i = 0; i < NL - 1; ++i) {
+  };
+  auto flux = [&](int i) { /* interface below layer i+1, i = 0..6 */
     const float rden = g.rden[i + 1];
     const float num = (s.smp[i + 1] - s.smp[i]) - (zq[i + 1] - zq[i]);
     const float nd = num * dhkdw[i];
-    q[i] = -hk[i] * num * rden;                 /* qout(I) == qin(I+1) */
-    qa[i] = fmaf(hk[i], dsmpdw[i], -nd) * rden; /* dqodw1(I) == dqidw0(I+1) */
+    q[i] = -hk[i] * num * rden;                     /* qout(I) == qin(I+1) */
+    qa[i] = fmaf(hk[i], dsmpdw[i], -nd) * rden;     /* dqodw1(I) == dqidw0(I+1) */
     qb[i] = -fmaf(hk[i], dsmpdw[i + 1], nd) * rden; /* dqodw2(I) == dqidw1(I+1) */
-  }
-  {
+  };
+  auto row0 = [&]() {
+    const float rmx = fmaf(-qflx_tran_veg_col, rs[0], qflx_infl - q[0]);
+    bet = g.dzdt[1] + qa[0];
+    if (bet == 0.0f) fault |= FAULT_PIVOT1;
+    rbet = MathFast::rcp(bet);
+    dwat2[0] = rmx * rbet;
+  };
+  auto row = [&](int i) { /* rows 2..8 (i = 1..7) */
+    const float rmx = fmaf(-qflx_tran_veg_col, rs[i], q[i - 1] - q[i]);
+    const float amx = -qa[i - 1];
+    const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
+    gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
+    bet = fmaf(-amx, gam[i], bmx);
+    minpiv = fminf(minpiv, fabsf(bet));
+    rbet = MathFast::rcp(bet);
+    dwat2[i] = fmaf(-amx, dwat2[i - 1], rmx) * rbet;
+  };
+
+  { /* :576-590: vol_eq(9), evaluated for every cell and selected by `deep` (see below) */
     const int i = NL - 1;
-    {
-      const float b = c.bsw(i), inv_ths = c.inv_ths(i);
-      const float s_node = fminf(1.0f, fmaxf(0.5f * fmaf(theta[i], inv_ths, 1.0f), 0.01f));
-      const float smp1 = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
-      const float zc9 = 0.5f * (zwtmm + g.zc[NL]);
-      /* 1/s_node and 1/(zc(9)-zc(8)) from one MUFU; the second factor is > 0 exactly for the
-       * cells (deep) whose results are kept below */
-      const float den9 = zc9 - g.zc[NL];
-      const float r9 = MathFast::rcp(s_node * den9);
-      const float rden = r9 * s_node;
-      const float dsmpdw1 = c.comp(2, i, 3) * smp1 * (r9 * den9);
-      const float num = (smp1 - s.smp[i]) - (zq[NL] - zq[i]);
-      const float nd = num * dhkdw[i];
-      q[i] = deep ? -hk[i] * num * rden : 0.0f;
-      qa[i] = deep ? fmaf(hk[i], dsmpdw[i], -nd) * rden : 0.0f;
-      qb[i] = deep ? -fmaf(hk[i], dsmpdw1, nd) * rden : 0.0f;
+    const float ths = c.ths(i), psi = c.psi(i), e1 = c.e1(i), inv_npsi = c.inv_npsi(i);
+    const float u = (zwtmm - g.zi[NL]) * inv_npsi;
+    const float a2 = 0.5f * (e1 - 1.0f), a3 = (1.0f / 3.0f) * (e1 - 2.0f), a4 = 0.25f * (e1 - 3.0f);
+    const float r_series = e1 * fmaf(u * a2, fmaf(u * a3, fmaf(u, a4, 1.0f), 1.0f), 1.0f);
+    const float r_direct = (fast_pow(1.0f + u, e1) - 1.0f) * MathFast::rcp(u);
+    const float r = (u < 0.03f) ? r_series : r_direct;
+    const float coefA = c.coef3(i) * (g.zi[NL] - g.zi[NL - 1]);
+    float vol = -coefA * inv_npsi * r;
+    vol = fminf(ths, fmaxf(vol, 0.0f));
+    const float z9 = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
+    zq[NL] = deep ? z9 : 0.0f;
+  }
+#pragma unroll
+  for (int P = 0; P < NL / 2; ++P) {
+    eq_layer(2 * P);
+    eq_layer(2 * P + 1);
+    hk_layer(2 * P);
+    hk_layer(2 * P + 1);
+    pair_rcp(2 * P);
+    if (P > 0) flux(2 * P - 1);
+    flux(2 * P);
+    if (P == 0) {
+      row0();
+    } else {
+      row(2 * P - 1);
+      row(2 * P);
     }
   }
-
-  /* Parts of Recharge/Drainage (:856-965) that do not depend on the solve are issued before
-   * it, so that their pow chains run behind the Thomas sweep instead of after it: the aquifer's
-   * specific yield, and for a water table inside the column the Darcy recharge and the
-   * specific yield of the layer that holds the table. */
-  const float rous_early = fast_specific_yield(c, NL - 1, zwtmm);
-  const float rrous_early = MathFast::rcp(rous_early);
+  { /* aquifer node :645-650 and its interface :737-753; inert when the table is in the column */
+    const int i = NL - 1;
+    const float b = c.bsw(i), inv_ths = c.inv_ths(i);
+    const float s_node = fminf(1.0f, fmaxf(0.5f * fmaf(theta[i], inv_ths, 1.0f), 0.01f));
+    const float smp1 = fmaxf(kSmpmin, c.psi(i) * fast_pow(s_node, -b));
+    const float zc9 = 0.5f * (zwtmm + g.zc[NL]);
+    const float den9 = zc9 - g.zc[NL];
+    const float r9 = MathFast::rcp(s_node * den9);
+    const float rden = r9 * s_node;
+    const float dsmpdw1 = c.comp(2, i, 3) * smp1 * (r9 * den9);
+    const float num = (smp1 - s.smp[i]) - (zq[NL] - zq[i]);
+    const float nd = num * dhkdw[i];
+    q[i] = deep ? -hk[i] * num * rden : 0.0f;
+    qa[i] = deep ? fmaf(hk[i], dsmpdw[i], -nd) * rden : 0.0f;
+    qb[i] = deep ? -fmaf(hk[i], dsmpdw1, nd) * rden : 0.0f;
+  }
+  row(NL - 1);
+  { /* aquifer row */
+    const float rmx = q[NL - 1];
+    const float amx = -qa[NL - 1];
+    const float bmx = fmaf(dz9, rdt, -qb[NL - 1]);
+    gam[NL] = qb[NL - 1] * rbet;
+    bet = fmaf(-amx, gam[NL], bmx);
+    minpiv = fminf(minpiv, fabsf(bet));
+    dwat2[NL] = fmaf(-amx, dwat2[NL - 1], rmx) * MathFast::rcp(bet);
+  }
+  /* for a water table inside the column the Darcy recharge and the specific yield of the
+   * layer holding the table do not depend on the solve either (issued before the back
+   * substitution; they read the NEW smp, :880) */
   float qcharge_early = 0.0f, sy_first = 0.02f;
   if (!deep) {
     const int jm = (jwt > 1 ? jwt : 1) - 1;
@@ -354,39 +389,6 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     qcharge_early = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
     sy_first = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
-  }
-  /* tridiagonal rows :661-799 fused with the Thomas forward sweep :806-827 */
-  float dwat2[NL + 1], gam[NL + 1];
-  float bet, rbet, minpiv;
-  const float4 rc = c.rootr4(0), rd = c.rootr4(1); /* re-read: cheaper than eight live registers */
-  const float rs[NL] = {rc.x, rc.y, rc.z, rc.w, rd.x, rd.y, rd.z, rd.w};
-  {
-    const float rmx = fmaf(-qflx_tran_veg_col, rs[0], qflx_infl - q[0]);
-    bet = g.dzdt[1] + qa[0];
-    if (bet == 0.0f) fault |= FAULT_PIVOT1;
-    rbet = MathFast::rcp(bet);
-    minpiv = 3.0e38f;
-    dwat2[0] = rmx * rbet;
-  }
-#pragma unroll
-  for (int i = 1; i < NL; ++i) {
-    const float rmx = fmaf(-qflx_tran_veg_col, rs[i], q[i - 1] - q[i]);
-    const float amx = -qa[i - 1];
-    const float bmx = (g.dzdt[i + 1] - qb[i - 1]) + qa[i];
-    gam[i] = qb[i - 1] * rbet; /* cmx(I-1)/BET */
-    bet = fmaf(-amx, gam[i], bmx);
-    minpiv = fminf(minpiv, fabsf(bet));
-    rbet = MathFast::rcp(bet);
-    dwat2[i] = fmaf(-amx, dwat2[i - 1], rmx) * rbet;
-  }
-  { /* aquifer row */
-    const float rmx = q[NL - 1];
-    const float amx = -qa[NL - 1];
-    const float bmx = fmaf(dz9, rdt, -qb[NL - 1]);
-    gam[NL] = qb[NL - 1] * rbet;
-    bet = fmaf(-amx, gam[NL], bmx);
-    minpiv = fminf(minpiv, fabsf(bet));
-    dwat2[NL] = fmaf(-amx, dwat2[NL - 1], rmx) * MathFast::rcp(bet);
   }
   if (minpiv == 0.0f) fault |= FAULT_PIVOT2; /* BET == 0 in some row :818 */
 #pragma unroll
