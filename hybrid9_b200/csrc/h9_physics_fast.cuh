@@ -391,13 +391,6 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     sy_first = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
   }
   if (minpiv == 0.0f) fault |= FAULT_PIVOT2; /* BET == 0 in some row :818 */
-#pragma unroll
-  for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
-
-  /* :845-850 */
-#pragma unroll
-  for (int i = 0; i < NL; ++i) s.h2o[i] = fmaf(dwat2[i], g.dz[i + 1], s.h2o[i]);
-
   /* recharge :856-904 */
   float qcharge;
   qcharge = deep ? dwat2[NL] * dz9 * rdt : qcharge_early;
@@ -439,6 +432,14 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   /* baseflow :1024-1118 */
   float rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
   rous = fast_specific_yield(c, NL - 1, zwtmm);
+  /* dwat2(9), the only unknown Recharge and Drainage read, is final after the forward sweep;
+   * the back substitution :828-830 and the update of h2osoi_liq :845-850 are issued here,
+   * behind the water-table update and the baseflow's exp / pow, just before baseflow
+   * touches h2osoi_liq */
+#pragma unroll
+  for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) s.h2o[i] = fmaf(dwat2[i], g.dz[i + 1], s.h2o[i]);
   if (jwt == NL) { /* jwt is not recomputed on this path */
     s.wa = fmaf(-rsub_top, dt, s.wa);
     s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
