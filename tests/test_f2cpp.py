@@ -206,3 +206,150 @@ def test_outside_the_subset_is_refused(stmt, why):
     with pytest.raises(f2cpp.TranslateError) as e:
         translate(stmt)
     assert why.split()[0].lower() in str(e.value).lower(), str(e.value)
+
+
+# ---- randomised expressions: the translator against an independent evaluator of the standard's rules ----
+
+class _Gen:
+    """Random expression trees over REAL a,b,c and INTEGER i,j,k.  `text` prints a tree with the
+    FEWEST parentheses Fortran's precedence allows, so the translator's parser has to rebuild the
+    tree; `value` evaluates the tree itself with the standard's typing (int/int truncates, mixed
+    operands promote to REAL, every REAL operation rounds to float32)."""
+    PREC = {"**": 5, "*": 4, "/": 4, "neg": 3, "+": 2, "-": 2}
+
+    def __init__(self, rng, env):
+        self.rng, self.env = rng, env
+
+    def tree(self, depth):
+        r = self.rng
+        if depth == 0 or r.random() < 0.25:
+            kind = r.integers(0, 4)
+            if kind == 0:
+                return ("var", str(r.choice(["a", "b", "c"])))
+            if kind == 1:
+                return ("var", str(r.choice(["i", "j", "k"])))
+            if kind == 2:
+                return ("rlit", str(r.choice(["0.5", "2.0", "1.25", "3.0E-1", "7.5"])))
+            return ("ilit", str(int(r.integers(1, 6))))
+        op = str(r.choice(["+", "-", "*", "/", "**", "neg", "max", "min", "abs"]))
+        if op == "neg":
+            return ("neg", self.tree(depth - 1))
+        if op == "abs":
+            return ("abs", self.tree(depth - 1))
+        if op in ("max", "min"):
+            return (op, self.tree(depth - 1), self.tree(depth - 1))
+        if op == "**":
+            return ("**", self.tree(depth - 1), ("ilit", str(int(r.integers(2, 4)))))
+        return (op, self.tree(depth - 1), self.tree(depth - 1))
+
+    def text(self, t, parent=0, right=False, first_term=True):
+        k = t[0]
+        if k == "var" or k in ("rlit", "ilit"):
+            return t[1]
+        if k in ("max", "min"):
+            return f"{k} ({self.text(t[1])}, {self.text(t[2])})"
+        if k == "abs":
+            return f"abs ({self.text(t[1])})"
+        if k == "neg":
+            # a sign is only legal at the start of a level-2 expression: parenthesise elsewhere
+            inner = "-" + self.text(t[1], self.PREC["*"], False)
+            return inner if (parent <= self.PREC["+"] and first_term and not right) else f"({inner})"
+        p = self.PREC[k]
+        if k == "**":
+            s = f"{self.text(t[1], p + 1)} ** {self.text(t[2], p, True)}"
+        else:
+            s = f"{self.text(t[1], p, False, first_term)} {k} {self.text(t[2], p + (0 if k in '+*' and False else 1), True, False)}"
+        need = p < parent or (p == parent and right)
+        return f"({s})" if need else s
+
+    def value(self, t):
+        import numpy as np
+        k = t[0]
+        if k == "var":
+            return self.env[t[1]]
+        if k == "rlit":
+            return np.float32(float(t[1]))
+        if k == "ilit":
+            return int(t[1])
+        if k == "neg":
+            v = self.value(t[1])
+            return -v
+        if k == "abs":
+            v = self.value(t[1])
+            return abs(v) if isinstance(v, int) else np.float32(abs(v))
+        a, b = self.value(t[1]), self.value(t[2])
+        if k == "**":
+            n = b
+            if isinstance(a, int):
+                return a ** n
+            y = a if n % 2 else np.float32(1.0)
+            x = a
+            n >>= 1
+            while n:
+                x = np.float32(x * x)
+                if n % 2:
+                    y = np.float32(y * x)
+                n >>= 1
+            return y
+        both_int = isinstance(a, int) and isinstance(b, int)
+        if not both_int:
+            a, b = np.float32(a), np.float32(b)
+        if k in ("max", "min"):
+            return (max if k == "max" else min)(a, b)
+        if k == "+":
+            return a + b if both_int else np.float32(a + b)
+        if k == "-":
+            return a - b if both_int else np.float32(a - b)
+        if k == "*":
+            return a * b if both_int else np.float32(a * b)
+        if both_int:
+            if b == 0:
+                raise ZeroDivisionError
+            q = abs(a) // abs(b)
+            return q if (a >= 0) == (b >= 0) else -q
+        if b == 0:
+            raise ZeroDivisionError
+        return np.float32(a / b)
+
+
+def test_random_expressions_follow_the_standard():
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    env = {"a": np.float32(1.75), "b": np.float32(-0.625), "c": np.float32(3.5), "i": 7, "j": -3, "k": 2}
+    gen = _Gen(rng, env)
+    cases = []
+    while len(cases) < 250:
+        t = gen.tree(4)
+        try:
+            with np.errstate(all="raise"):
+                v = gen.value(t)
+        except (ZeroDivisionError, FloatingPointError, OverflowError):
+            continue
+        if isinstance(v, int):
+            if abs(v) > 10 ** 8:
+                continue
+        elif not np.isfinite(v) or abs(v) > 1e30:
+            continue
+        cases.append((gen.text(t), v))
+    # one program: r(n) = expression n (REAL target: integer results are converted on assignment)
+    decl = "real :: a, b, c\ninteger :: i, j, k\nreal :: r (%d)\n" % len(cases)
+    body = "a = 1.75\nb = -0.625\nc = 3.5\ni = 7\nj = -3\nk = 2\n" + \
+        "\n".join(f"r ({n + 1}) = {txt}" for n, (txt, _) in enumerate(cases))
+    scope = f2cpp.Scope("t")
+    f2cpp.collect_declarations([(n + 1, f2cpp.fold_case(s)) for n, s in enumerate(decl.strip().split("\n"))],
+                               "decl", scope, "")
+    d, ctor = f2cpp.member_declarations(scope)
+    unit = f2cpp.Unit("run", "snippet", scope, [(100 + n, f2cpp.fold_case(s)) for n, s in enumerate(body.split("\n"))])
+    src = ("#include \"%s\"\n#include <cstdio>\nstruct T {\n%s\n  T() {\n%s\n  }\n  [[noreturn]] void f2c_stop(int, int) "
+           "{ std::exit(1); }\n  void run() {\n%s\n  }\n};\nint main() { T t; t.run(); for (int n = 1; n <= %d; ++n) "
+           "std::printf(\"%%.9g\\n\", (double)t.r_(n)); }\n"
+           % (os.path.join(ROOT, "oracle", "f2c_rt.h"), "\n".join(d), "\n".join(ctor), "\n".join(unit.translate()),
+              len(cases)))
+    with tempfile.TemporaryDirectory() as tmp:
+        cpp, exe = os.path.join(tmp, "t.cpp"), os.path.join(tmp, "t")
+        open(cpp, "w").write(src)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2C_BOUNDS", "-o", exe, cpp], check=True)
+        got = [np.float32(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert len(got) == len(cases)
+    bad = [(txt, float(np.float32(v)), float(g)) for (txt, v), g in zip(cases, got) if np.float32(v) != g]
+    assert not bad, bad[:5]
