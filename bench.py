@@ -19,11 +19,17 @@ PGF-shaped forcing (hybrid9_b200/synth.py).
          oracle/f2cpp.py and compiled -O3 (oracle/_ref; kind "reference"; the image has no
          Fortran compiler), on all host cores, bounded sample; the hand-written port beside it.
 
-`--impl reference` times that CPU implementation alone (rank 0), same metric/config.
-Multi-GPU: one process per GPU (torchrun), each rank a full 0.5 deg block
-(weak scaling; `--scaling strong` shards one block in latitude bands instead);
-the only collectives are the per-year annual-mean all-gather and the FP64
-budget all-reduce, inside the timed region.
+  roofline.pipe  the binding roofline: issue slots and MUFU of the fused kernel, from the
+         instruction counts of the committed ncu capture (profiles/pipe.json).
+
+`--impl reference` times that CPU implementation alone (rank 0), same metric/config; both
+CPU figures time the SAME fixed sample (cpu_sample) and report the median of the repeats.
+Multi-GPU (torchrun, one process per GPU): ONE 0.5 deg grid sharded in contiguous latitude
+bands (`--scaling strong`, the default: BASELINE.json's metric is one global grid on
+1/2/4/8 GPUs); the replicated-grid number (every rank a full block, `--scaling weak`) is
+measured in the same run and carried as the `weak` sub-record.  The only collectives are the
+per-year annual-mean all-gather and the FP64 budget all-reduce, issued by the library itself
+(h9_annual_collective: NCCL on the ctx's stream) inside the timed region.
 """
 from __future__ import annotations
 
@@ -51,7 +57,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling sub-record at N>1")
     ap.add_argument("--grid", default="0.5", choices=["0.5", "0.25", "regional", "tiny", "band8"])
     ap.add_argument("--days", type=int, default=365)
     ap.add_argument("--nisurf", type=int, default=48)
@@ -60,7 +67,7 @@ def parse_args():
     ap.add_argument("--tile-days", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-repeats", type=int, default=5)
     return ap.parse_args()
 
 
@@ -185,28 +192,58 @@ def cpu_engines(world, forcing, ncell, nisurf, cores):
     return eng
 
 
-def cpu_baseline(world, forcing, nisurf, seconds):
-    """Time the reference's CPU implementation on all host cores over a bounded sample of the
-    same workload (first cells of the block, first days of the year).  `value` is the translated
-    reference when it is present (kind "reference"); the hand-written port is timed beside it."""
+CPU_SAMPLE_CELLS_PER_CORE = 1024
+CPU_SAMPLE_DAYS = 24
+
+
+def cpu_sample(args):
+    """The ONE bounded sample both CPU legs time: the first 1024 x cores land cells of the
+    0.5 deg mask (reference iteration order) x 24 days x NISURF sub-steps, INIT state,
+    forcing seed 9.  Fixed cells x days, so `cpu_baseline` of the graft arm and the line of
+    `--impl reference` time the same work."""
+    from hybrid9_b200 import synth
+    g = grid_spec("0.5")
+    world = synth.make_world(nx=g["nx"], ny=g["ny"], n_land=g["n_land"], seed=9)
     cores = os.cpu_count() or 1
-    ncell = int(min(world.land.sum(), 1024 * cores))
-    days_avail = forcing["tas"].shape[0]
-    eng = cpu_engines(world, forcing, ncell, nisurf, cores)
+    ncell = int(min(world.land.sum(), CPU_SAMPLE_CELLS_PER_CORE * cores))
+    cw = synth.compact_world(world, ncell)
+    forcing = synth.make_forcing(cw, CPU_SAMPLE_DAYS, seed=9)
+    return cw, forcing, ncell, cores
+
+
+def cpu_time_sample(args, repeats, warm, kinds=("reference", "port")):
+    """Median-of-repeats rate of each CPU engine on cpu_sample().  Returns {kind: {...}}."""
+    cw, forcing, ncell, cores = cpu_sample(args)
+    eng = cpu_engines(cw, forcing, ncell, args.nisurf, cores)
+    nd = CPU_SAMPLE_DAYS
+    units = ncell * nd * args.nisurf
     out = {}
-    for kind, (run, what) in eng.items():
-        budget = seconds if len(eng) == 1 else seconds / 2
-        run(min(2, days_avail))  # first touch of the arrays, thread start-up
-        rate = ncell * min(8, days_avail) * nisurf / run(min(8, days_avail))
-        nd = int(max(2, min(days_avail, budget * rate / (ncell * nisurf))))
-        dt = run(nd)
-        out[kind] = {"value": ncell * nd * nisurf / dt, "seconds": dt,
-                     "sample": f"{ncell} land cells x {nd} days x {nisurf} sub-steps, cell-outer "
-                               f"loop order; {what}"}
+    for kind in kinds:
+        if kind not in eng:
+            continue
+        run, what = eng[kind]
+        for _ in range(max(1, warm)):  # first touch of the arrays, thread start-up
+            run(nd)
+        ts = sorted(run(nd) for _ in range(max(3, repeats)))
+        med = ts[len(ts) // 2]
+        out[kind] = {"value": units / med, "seconds_median": med, "seconds_min": ts[0],
+                     "seconds_max": ts[-1], "spread": (ts[-1] - ts[0]) / med, "repeats": len(ts),
+                     "units_per_repeat": units,
+                     "sample": f"{ncell} land cells x {nd} days x {args.nisurf} sub-steps (fixed), "
+                               f"median of {len(ts)} repeats, cell-outer loop order; {what}"}
+    return out, cores
+
+
+def cpu_baseline(args):
+    """Time the reference's CPU implementation on all host cores over the fixed sample.
+    `value` is the translated reference when it is present (kind "reference"); the
+    hand-written port is timed beside it."""
+    out, cores = cpu_time_sample(args, args.cpu_repeats, 1)
     kind = "reference" if "reference" in out else "port"
     res = {"value": out[kind]["value"], "unit": UNIT, "cores": cores, "kind": kind,
-           "sample": out[kind]["sample"], "seconds": out[kind]["seconds"]}
-    if kind == "reference":
+           "sample": out[kind]["sample"], "seconds": out[kind]["seconds_median"],
+           "spread": out[kind]["spread"], "repeats": out[kind]["repeats"]}
+    if kind == "reference" and "port" in out:
         res["port_value"] = out["port"]["value"]
         res["port_sample"] = out["port"]["sample"]
     return res
@@ -227,41 +264,28 @@ def build_world(args):
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path alone (the
     translated Fortran when oracle/_ref is present, else the hand-written port), rank 0 only,
-    all host threads, each step a bounded sample of the workload."""
+    all host threads; each step is one pass over the fixed sample of cpu_sample()."""
     if rank != 0:
         return
-    from hybrid9_b200 import synth
-    world, label = build_world(args)
-    cores = os.cpu_count() or 1
-    ncell = int(min(world.land.sum(), 1024 * cores))  # same sample as the graft arm's cpu_baseline
-    sample_days = min(args.days, 120)
-    cw = synth.compact_world(world, ncell)
-    forcing = synth.make_forcing(cw, sample_days, seed=9)
-    eng = cpu_engines(cw, forcing, ncell, args.nisurf, cores)
-    kind = "reference" if "reference" in eng else "port"
-    run, what = eng[kind]
-    # size one step to a few seconds of CPU work (whole run within ~2 minutes)
-    run(2)
-    rate = ncell * 8 * args.nisurf / run(min(8, sample_days))
-    per_step = max(1.0, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
-    nd = int(max(2, min(sample_days, per_step * rate / (ncell * args.nisurf))))
-    for _ in range(args.warmup):
-        run(nd)
-    dt = 0.0
-    for _ in range(args.steps):
-        dt += run(nd)
-    units = ncell * nd * args.nisurf * args.steps
-    value = units / dt
-    sample = (f"{ncell} land cells x {nd} days x {args.nisurf} sub-steps per step, cell-outer "
-              f"loop order; {what}")
+    label = grid_spec(args.grid)["label"]
+    kinds = ("reference",)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_py
+    if not ref_py.available("o3"):
+        kinds = ("port",)
+    out, cores = cpu_time_sample(args, args.steps, max(1, args.warmup), kinds=kinds)
+    kind = kinds[0]
+    r = out[kind]
+    value, sample = r["value"], r["sample"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": r["repeats"], "warmup": max(1, args.warmup), "ms_per_step": 1e3 * r["seconds_median"],
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{label}, {args.days} d x {args.nisurf} sub-steps "
                                f"(bounded CPU sample: {sample})"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "spread": r["spread"], "repeats": r["repeats"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,10 +318,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from hybrid9_b200 import H9, MATH_EXACT, MATH_FAST, synth
-    from hybrid9_b200.host import pinned_empty
-    from hybrid9_b200.state import init_state
-    from hybrid9_b200 import distributed as h9d
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the HYDROLOGY/GROW path has no CPU fallback")
@@ -307,22 +327,112 @@ def main():
     if multi:
         dist.init_process_group("nccl", device_id=dev)
 
+    res = measure(args, args.scaling, rank, local_rank, world_size, dev, e2e=not args.no_e2e,
+                  steps=args.steps, sample_clocks=True)
+    weak = None
+    if multi and args.scaling == "strong" and not args.no_weak:
+        # the replicated-grid number of the same run: every rank steps a full block
+        w = measure(args, "weak", rank, local_rank, world_size, dev, e2e=False,
+                    steps=min(args.steps, 5), sample_clocks=False)
+        weak = {"value": w["value"], "unit": UNIT, "ms_per_step": w["ms_per_step"], "steps": w["steps"],
+                "land_cells_per_gpu": w["n_land_all"], "scaling": "weak",
+                "note": "every rank steps its own full 0.5deg block (replicas); secondary"}
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline(args)
+        except Exception as ex:  # the checker is test infrastructure; never fail the bench on it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        nd, nis = args.days, args.nisurf
+        n_land_all = res["n_land_all"]
+        sharded = multi and args.scaling == "strong"
+        line = {
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": (f"{res['label']} sharded in contiguous latitude bands over "
+                                    f"{world_size} GPUs: {sum(n_land_all)} land cells x {nd} days x "
+                                    f"{nis} sub-steps per step") if sharded else
+                                   (f"{res['label']}: {n_land_all[0]} land cells x {nd} days x {nis} "
+                                    f"sub-steps per step" + (" per GPU" if multi else "")),
+                       "land_cells_per_gpu": n_land_all, "days_per_step": nd, "nisurf": nis,
+                       "math": args.math, "simulated_years": res["years"],
+                       "share_cells_water_table_in_soil_column_at_end": round(res["shallow"], 4),
+                       "l2": "forcing stream (689 MB/step at 0.5deg) exceeds L2; state is "
+                             "register/L2 resident by design",
+                       "kernel_variant": res["variant"],
+                       "parallelism": f"dp{world_size} latitude bands, no data-path collective; per "
+                                      "simulated year one FP64 budget all-reduce and one all-gather "
+                                      "of the annual means (h9_annual_collective, NCCL on the "
+                                      "library's stream)" if multi else "single GPU"},
+            "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": res["e2e"],
+            "gpu_launches": res["launches"], "clocks": res["clocks"], "wall_s_timed": res["wall"],
+        }
+        if weak is not None:
+            line["weak"] = weak
+        emit(line)
+    if multi:
+        dist.destroy_process_group()
+
+
+def pipe_roofline(variant, units_rank, kern_ms, clocks):
+    """The binding roofline of the fused kernel: issue slots (one warp instruction per
+    scheduler per cycle) and the MUFU unit (8 cycles per warp instruction per scheduler),
+    from the executed-instruction counts of the committed ncu capture (profiles/pipe.json),
+    at the SM clock sampled during the run."""
+    pf = os.path.join(ROOT, "profiles", "pipe.json")
+    if not os.path.exists(pf):
+        return None
+    try:
+        with open(pf) as f:
+            pj = json.load(f)
+        k = pj["kernels"].get(variant) or pj["kernels"][pj["default"]]
+        mhz = (clocks or {}).get("sm_mhz") or pj.get("sm_mhz", 1965.0)
+        sched = pj.get("schedulers", 148 * 4)
+        wsub = units_rank / float(k["cell_steps_per_warp_substep"])  # warp-sub-steps per launch
+        issue_ms = wsub * k["warp_inst_per_substep"] / (sched * mhz * 1e3)
+        mufu_ms = wsub * k["mufu_per_substep"] * 8.0 / (sched * mhz * 1e3)
+        floor_ms = max(issue_ms, mufu_ms)
+        return {"bound": "issue" if issue_ms >= mufu_ms else "mufu",
+                "warp_inst_per_substep": k["warp_inst_per_substep"],
+                "mufu_per_substep": k["mufu_per_substep"],
+                "cell_steps_per_warp_substep": k["cell_steps_per_warp_substep"],
+                "issue_floor_ms": issue_ms, "mufu_floor_ms": mufu_ms, "floor_ms": floor_ms,
+                "frac": floor_ms / kern_ms if kern_ms > 0 else None, "sm_mhz": mhz,
+                "schedulers": sched, "source": k.get("source")}
+    except Exception as ex:
+        return {"error": str(ex)}
+
+
+def measure(args, scaling, rank, local_rank, world_size, dev, e2e, steps, sample_clocks):
+    """One workload (the whole grid on one GPU, a latitude band of it, or a replica) through
+    the device-resident and the end-to-end entry; returns the numbers of this rank's line."""
+    import torch
+    import torch.distributed as dist
+    from hybrid9_b200 import H9, MATH_EXACT, MATH_FAST, synth
+    from hybrid9_b200.host import pinned_empty
+    from hybrid9_b200.state import init_state
+    from hybrid9_b200 import distributed as h9d
+
+    multi = world_size > 1
     world, label = build_world(args)
-    lat_s = 1
-    if multi and args.scaling == "strong":
-        world, lat_s, _, n_land_all = h9d.shard_world(world, rank, world_size)
+    if multi and scaling == "strong":
+        world, _, _, _ = h9d.shard_world(world, rank, world_size)
     nd, nis = args.days, args.nisurf
     nc = int(world.land.sum())
-    n_land_all = [nc] * world_size
-    if multi:
-        t = torch.tensor([nc], device=dev, dtype=torch.int64)
-        parts = [torch.zeros_like(t) for _ in range(world_size)]
-        dist.all_gather(parts, t)
-        n_land_all = [int(p.item()) for p in parts]
 
-    # host forcing exactly as READ_PGF leaves it, in pinned memory
+    # host forcing exactly as READ_PGF leaves it, in pinned memory (pageable for the
+    # device-resident-only weak sub-record)
     names = ("tas", "rlds", "rsds", "huss", "ps", "pr", "rhs")
-    forcing = {k: pinned_empty((nd, world.ny, world.nx)) for k in names}
+    if e2e:
+        forcing = {k: pinned_empty((nd, world.ny, world.nx)) for k in names}
+    else:
+        forcing = {k: np.empty((nd, world.ny, world.nx), np.float32) for k in names}
     synth.make_forcing(world, nd, seed=9 + rank, out=forcing)
 
     h = H9(local_rank)
@@ -333,14 +443,19 @@ def main():
     h.set_soil(world.soil_tex, world.theta_s, world.hksat, world.bsw, world.psi_s, world.fmax)
     assert h.num_land == nc
     h.set_state(init_state(world.soil_tex, world.theta_s, synth.ZI_DRIVER), with_smp=False)
+    n_land_all = [nc]
+    if multi:
+        # the library's own NCCL communicator; torch.distributed only carries the 128-byte id
+        n_land_all = [int(x) for x in h9d.comm_init_from_torch(h, device=dev)]
     d_forc, day_stride, plane_stride = h.pack_forcing(forcing, nd)
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
     year = [0]
 
     def collective(iy):
         if multi:
-            parts, budget = h9d.h9_annual_collective(h, iy, n_land_all, device=dev)
-            if year[0] <= 1:  # sanity of the gathered view, outside the hot loop's steady state
+            h.annual_collective(iy)  # stream-ordered, no host sync
+            if year[0] <= 1:  # sanity of the gathered view, outside the steady state
+                parts, budget = h9d.fetch_gathered(h, iy, n_land_all)
                 assert [int(p.shape[1]) for p in parts] == n_land_all
                 assert int(round(float(budget[5]))) == sum(n_land_all) and float(budget[7]) == 0.0
 
@@ -362,7 +477,7 @@ def main():
         collective(iy)
         return ann
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, nsteps, warmup, clocks=False):
         for _ in range(warmup):
             fn()
         h.synchronize()
@@ -370,14 +485,14 @@ def main():
         if multi:
             dist.barrier()
         h.reset_counters()
-        cs = ClockSampler(local_rank) if sample_clocks else None
+        cs = ClockSampler(local_rank) if clocks else None
         if cs:
             cs.start()
             time.sleep(0.25)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(nsteps):
             fn()
         e1.record(stream)
         h.synchronize()
@@ -386,30 +501,32 @@ def main():
         if multi:
             dist.barrier()
         ms = max(e0.elapsed_time(e1), 0.0)
-        clocks = cs.stop() if cs else None
+        ck = cs.stop() if cs else None
         cnt = h.counters()
         if multi:
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms, wall, cnt, clocks
+        return ms, wall, cnt, ck
 
     units_rank = nc * nd * nis
     units_all = sum(n_land_all) * nd * nis
 
-    ms, wall, cnt, clocks = timed(step_device, args.steps, max(args.warmup, 3), sample_clocks=True)
-    ms_per_step = ms / args.steps
+    ms, wall, cnt, clocks = timed(step_device, steps, max(args.warmup, 3), clocks=sample_clocks)
+    ms_per_step = ms / steps
     value = units_all / (ms_per_step * 1e-3)
-    kern_ms = cnt["step_kernel_ms"] / max(1, args.steps)  # fused kernel, CUDA events, this rank
+    kern_ms = cnt["step_kernel_ms"] / max(1, steps)  # fused kernel, CUDA events, this rank
     peak, peak_src = peaks()
     achieved = units_rank * BYTES_PER_CELL_STEP / (kern_ms * 1e-3) / 1e9
+    variant = h.kernel_variant()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "h9::days_kernel_fast" if args.math == "fast" else "h9::days_kernel<MathExact>",
-                "kernel_ms_per_launch": kern_ms, "launches_per_step": cnt["launches"] / args.steps,
+                "frac": achieved / peak, "traffic": None, "kernel": variant,
+                "kernel_ms_per_launch": kern_ms, "launches_per_step": cnt["launches"] / steps,
                 "algorithmic_bytes_per_unit": BYTES_PER_CELL_STEP, "peak_source": peak_src,
-                "note": "algorithmic roofline of a per-sub-step operator; the fused kernel keeps "
-                        "state in registers, real DRAM traffic is the forcing stream (see "
-                        "profiles/), the binding limiters are the FP32/MUFU pipes"}
+                "note": "algorithmic roofline of a per-sub-step operator (this rank's shard "
+                        "against one GPU's peak); the fused kernel keeps state in registers, real "
+                        "DRAM traffic is the forcing stream (see profiles/), the binding limiters "
+                        "are issue slots and the MUFU pipe: see `pipe`"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -420,55 +537,28 @@ def main():
             roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
+    roofline["pipe"] = pipe_roofline(variant, units_rank, kern_ms, clocks)
     launches = cnt["launches"]
 
-    e2e = None
-    if not args.no_e2e:
-        ems, ewall, ecnt, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
-        e_ms = max(ems, ewall * 1e3) / args.steps
-        e2e = {"value": units_all / (e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": ecnt["h2d_bytes"] // args.steps,
-               "d2h_bytes_per_step": ecnt["d2h_bytes"] // args.steps,
-               "ms_per_step": e_ms, "gpu_launches": ecnt["launches"],
-               "api": "h9_run_days (pinned host forcing as READ_PGF leaves it) + h9_get_annual"}
-
-    cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu:
-        try:
-            cpu = cpu_baseline(world, forcing, nis, args.cpu_seconds)
-        except Exception as ex:  # the checker is test infrastructure; never fail the bench on it
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"failed: {ex}"}
+    e2e_rec = None
+    if e2e:
+        ems, ewall, ecnt, _ = timed(step_e2e, steps, max(args.warmup, 3))
+        e_ms = max(ems, ewall * 1e3) / steps
+        e2e_rec = {"value": units_all / (e_ms * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": ecnt["h2d_bytes"] // steps,
+                   "d2h_bytes_per_step": ecnt["d2h_bytes"] // steps,
+                   "ms_per_step": e_ms, "gpu_launches": ecnt["launches"],
+                   "api": "h9_run_days (pinned host forcing as READ_PGF leaves it) + h9_get_annual"
+                          + (" + h9_annual_collective" if multi else "")}
 
     # regime of the final state (outside the timed region): share of cells whose water table
     # is inside the soil column (jwt < 8), which take the branchier Drainage path
     st_end = h.get_state()
-    land_mask_ = world.land
-    shallow = float((st_end.zwt[land_mask_] <= synth.ZI_DRIVER[8] / 1000.0).mean()) if nc else 0.0
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{label}: {nc} land cells x {nd} days x {nis} sub-steps per "
-                                   f"step per GPU" if args.scaling == "weak" else
-                                   f"{label} sharded in latitude bands: {sum(n_land_all)} land cells "
-                                   f"x {nd} days x {nis} sub-steps per step",
-                       "land_cells_per_gpu": n_land_all, "days_per_step": nd, "nisurf": nis,
-                       "math": args.math, "simulated_years": year[0],
-                       "share_cells_water_table_in_soil_column_at_end": round(shallow, 4),
-                       "l2": "forcing stream (689 MB/step at 0.5deg) exceeds L2; state is "
-                             "register/L2 resident by design",
-                       "parallelism": f"dp{world_size} latitude bands, no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "wall_s_timed": wall,
-        }
-        emit(line)
+    shallow = float((st_end.zwt[world.land] <= synth.ZI_DRIVER[8] / 1000.0).mean()) if nc else 0.0
     h.close()
-    if multi:
-        dist.destroy_process_group()
+    return {"value": value, "ms_per_step": ms_per_step, "steps": steps, "n_land_all": n_land_all,
+            "roofline": roofline, "e2e": e2e_rec, "launches": launches, "clocks": clocks,
+            "wall": wall, "years": year[0], "shallow": shallow, "label": label, "variant": variant}
 
 
 if __name__ == "__main__":

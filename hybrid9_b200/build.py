@@ -22,10 +22,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = {
     "h9_kernels_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"],
     "h9_kernels_fast.cu": ["-fmad=false"],  # FMAs are explicit: every launch variant gives the same bits
+    "h9_kernels_pair.cu": ["-fmad=false"],  # two lanes per cell for small shards (H9_MATH_FAST)
     "h9_pack.cu": [],
     "h9_api.cu": [],
 }
-HEADERS = ["h9_physics.h", "h9_physics_fast.cuh", "h9_device.h", "h9_kernels.cuh"]
+HEADERS = ["h9_physics.h", "h9_physics_fast.cuh", "h9_physics_pair.cuh", "h9_device.h", "h9_kernels.cuh"]
 
 
 def _nvcc() -> str:

@@ -9,6 +9,8 @@
  * include/h9gpu.h for the per-entry citations.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> /* types and prototypes only: libnccl is dlopen'ed by h9_comm_init */
 
 #include <algorithm>
 #include <cstdio>
@@ -35,6 +37,7 @@ struct h9_ctx {
   size_t ngrid = 0;
   int math_mode = H9_MATH_FAST;
   int tile_days = 8, block = 1064; /* 64 threads/block, 128-register variant */
+  int pair_max_cells = -1;         /* shards up to this size step with two lanes per cell; -1: auto */
   /* h9_run_days ingest (env H9_INGEST): 3 hostread (default; page-locked arrays are read in
    * place by the stepping kernel, pageable ones fall back to gather), 0 gather, 1 pack,
    * 2 zerocopy pack */
@@ -63,6 +66,14 @@ struct h9_ctx {
   float* d_step_forcing = nullptr; /* [7][ncs] for the fine-grained entries */
   float* d_diag = nullptr;         /* [12][ncs] + jwt */
   double* d_budget = nullptr;
+  /* multi-GPU (h9_comm_init): one ctx per GPU, NCCL on the ctx's own stream */
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  std::vector<int64_t> land_of_rank, stride_of_rank; /* nc and ncs of every rank */
+  float* d_gather = nullptr;      /* [sum_r 13*ncs_r]: every rank's annual planes of one year */
+  double* d_budget_all = nullptr; /* [nyr][8]: all-reduced budget of every year slot */
+  size_t gather_elems = 0;
+  int gathered_year = 0;
   /* counters */
   int64_t launches = 0, h2d = 0, d2h = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
@@ -101,8 +112,10 @@ int dev_alloc(h9_ctx* ctx, T** p, size_t n, bool track = true) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
   if (e != cudaSuccess) return fail(ctx, H9_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
-  if (e != cudaSuccess) return fail(ctx, H9_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  /* on the ctx's own stream: it is non-blocking, so a memset on the legacy stream would not be
+   * ordered before the uploads and kernels that follow */
+  e = cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+  if (e != cudaSuccess) return fail(ctx, H9_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
   *p = (T*)q;
   if (track) ctx->allocs.push_back(q);
   return 0;
@@ -130,6 +143,21 @@ void free_land(h9_ctx* ctx) {
   ctx->have_soil = false;
 }
 
+/* fast mode: two lanes per cell (h9_kernels_pair.cu) when forced (block 4000) or when the
+ * shard leaves at most one 16-cell warp per scheduler */
+bool use_pair(const h9_ctx* ctx) {
+  if (ctx->math_mode != H9_MATH_FAST) return false;
+  if (ctx->block >= 4000) return true;
+  if (ctx->block != 1064) return false;
+  int limit = ctx->pair_max_cells;
+  if (limit < 0) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    limit = nsm * 4 * 16;
+  }
+  return ctx->dev.nc <= limit;
+}
+
 int set_device(h9_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   return 0;
@@ -151,8 +179,24 @@ cudaEvent_t get_event(h9_ctx* ctx) {
     return e;
   }
   cudaEvent_t e = nullptr;
-  cudaEventCreate(&e);
+  if (cudaEventCreate(&e) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr; /* the launch goes ahead untimed */
+  }
   return e;
+}
+
+/* fold finished timing pairs into step_ms and recycle their events; called where the stream
+ * has just been synchronised, so a host loop that never asks for the time
+ * keeps a bounded number of live events */
+void fold_timing(h9_ctx* ctx) {
+  for (auto& pr : ctx->timing) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) ctx->step_ms += ms;
+    ctx->event_pool.push_back(pr.first);
+    ctx->event_pool.push_back(pr.second);
+  }
+  ctx->timing.clear();
 }
 
 ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stride) {
@@ -165,16 +209,25 @@ ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stri
 int launch_days(h9_ctx* ctx, int ndays, const int32_t* d_yi, const ForcingView& fv,
                 const int32_t* d_cell_index = nullptr) {
   cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
-  CK(cudaEventRecord(e0, ctx->stream));
+  const bool timed = e0 && e1;
+  if (timed) CK(cudaEventRecord(e0, ctx->stream));
   if (ctx->math_mode == H9_MATH_EXACT) {
     CKL(launch_days_exact(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, fv, ctx->cur_year, ctx->nt,
                           ctx->step_counter, ctx->block, d_cell_index));
+  } else if (use_pair(ctx)) {
+    CKL(launch_days_pair(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, fv, ctx->cur_year, ctx->nt,
+                         ctx->step_counter, d_cell_index));
   } else {
     CKL(launch_days_fast(ctx->stream, ctx->dev, ctx->geo, ndays, d_yi, fv, ctx->cur_year, ctx->nt,
                          ctx->step_counter, ctx->block, d_cell_index));
   }
-  CK(cudaEventRecord(e1, ctx->stream));
-  ctx->timing.emplace_back(e0, e1);
+  if (timed) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->timing.emplace_back(e0, e1);
+  } else {
+    if (e0) ctx->event_pool.push_back(e0);
+    if (e1) ctx->event_pool.push_back(e1);
+  }
   return 0;
 }
 
@@ -208,6 +261,7 @@ int read_any_fault(h9_ctx* ctx, uint32_t* any) {
   CK(cudaMemcpyAsync(any, ctx->dev.any_fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->d2h += 4;
+  if (ctx->timing.size() > 32) fold_timing(ctx);
   return 0;
 }
 
@@ -348,7 +402,9 @@ int h9_create(h9_ctx** out, int device_id) {
     ctx->zero_copy = true;
   }
   const char* bl = getenv("H9_BLOCK");
-  if (bl && (atoi(bl) == 2000 || atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
+  if (bl && (atoi(bl) == 2000 || atoi(bl) == 4000 || atoi(bl) % 1000 == 32 || atoi(bl) % 1000 == 64 || atoi(bl) % 1000 == 128)) ctx->block = atoi(bl);
+  const char* pm = getenv("H9_PAIR_MAX_CELLS");
+  if (pm) ctx->pair_max_cells = atoi(pm);
   *out = ctx;
   return H9_OK;
 }
@@ -357,6 +413,7 @@ int h9_destroy(h9_ctx* ctx) {
   if (!ctx) return H9_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  h9_comm_destroy(ctx);
   free_land(ctx);
   if (ctx->d_year_index) cudaFree(ctx->d_year_index);
   for (auto& pr : ctx->timing) {
@@ -415,7 +472,7 @@ int h9_set_option(h9_ctx* ctx, int option, int value) {
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block) {
   if (!ctx) return H9_ERR_ARG;
   if (tile_days > 0) ctx->tile_days = tile_days;
-  if (block == 2000 || block % 1000 == 32 || block % 1000 == 64 || block % 1000 == 128) ctx->block = block;
+  if (block == 2000 || block == 4000 || block % 1000 == 32 || block % 1000 == 64 || block % 1000 == 128) ctx->block = block;
   return H9_OK;
 }
 
@@ -488,7 +545,7 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   d.bsw = bs;
   d.psi_s = ps;
   d.fmax = fm;
-  CK(cudaMemset(d.first_key, 0xFF, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d.first_key, 0xFF, sizeof(unsigned long long), ctx->stream));
   std::vector<float> h;
   /* padding cells get a benign copy of the last land cell's parameters */
   auto up8 = [&](const float* src, float* dst) -> int {
@@ -828,6 +885,13 @@ int h9_clear_fault(h9_ctx* ctx) {
 
 void* h9_stream(h9_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+const char* h9_kernel_variant(h9_ctx* ctx) {
+  if (!ctx) return "";
+  if (ctx->math_mode == H9_MATH_EXACT) return "h9::days_kernel<MathExact,64,1>";
+  if (use_pair(ctx)) return "h9::days_kernel_pair<128>";
+  return days_variant_fast(ctx->dev.nc, ctx->block);
+}
+
 int h9_synchronize(h9_ctx* ctx) {
   if (!ctx) return H9_ERR_ARG;
   if (set_device(ctx)) return H9_ERR_CUDA;
@@ -854,13 +918,7 @@ double h9_step_kernel_ms(h9_ctx* ctx) {
   if (!ctx) return -1.0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& pr : ctx->timing) {
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) ctx->step_ms += ms;
-    ctx->event_pool.push_back(pr.first);
-    ctx->event_pool.push_back(pr.second);
-  }
-  ctx->timing.clear();
+  fold_timing(ctx);
   return ctx->step_ms;
 }
 
@@ -898,6 +956,9 @@ int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const fl
   if (ctx->math_mode == H9_MATH_EXACT) {
     CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
                                     ctx->step_counter, diag));
+  } else if (use_pair(ctx)) {
+    CKL(launch_hydrology_step_pair(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
+                                   ctx->step_counter, diag));
   } else {
     CKL(launch_hydrology_step_fast(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
                                    ctx->step_counter, diag));
@@ -1036,6 +1097,234 @@ int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const 
     lat_count[r] = y - y0;
     if (n_land) n_land[r] = mine;
   }
+  return H9_OK;
+}
+
+} /* extern "C" */
+
+/* ---- multi-GPU: NCCL behind the C ABI ------------------------------------------------- */
+
+namespace {
+
+/* libnccl is loaded on first use so that libh9gpu.so itself has no NCCL dependency (a
+ * single-GPU Fortran host needs none).  A process that already holds a libnccl.so.2 (MPI
+ * launcher, torch) gets that copy: dlopen matches the loaded SONAME. */
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string err;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  const char* names[] = {getenv("H9_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+    api.err = dlerror();
+  }
+  if (!api.lib) return &api;
+#define H9_NCCL_SYM(field, sym)                                 \
+  api.field = (decltype(api.field))dlsym(api.lib, #sym);        \
+  if (!api.field) {                                             \
+    api.err = "libnccl: missing symbol " #sym;                  \
+    dlclose(api.lib);                                           \
+    api.lib = nullptr;                                          \
+    return &api;                                                \
+  }
+  H9_NCCL_SYM(GetUniqueId, ncclGetUniqueId)
+  H9_NCCL_SYM(CommInitRank, ncclCommInitRank)
+  H9_NCCL_SYM(CommDestroy, ncclCommDestroy)
+  H9_NCCL_SYM(AllReduce, ncclAllReduce)
+  H9_NCCL_SYM(AllGather, ncclAllGather)
+  H9_NCCL_SYM(Broadcast, ncclBroadcast)
+  H9_NCCL_SYM(GroupStart, ncclGroupStart)
+  H9_NCCL_SYM(GroupEnd, ncclGroupEnd)
+  H9_NCCL_SYM(GetErrorString, ncclGetErrorString)
+#undef H9_NCCL_SYM
+  return &api;
+}
+
+#define CKN(call)                                                                          \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != ncclSuccess)                                                                 \
+      return fail(ctx, H9_ERR_NCCL, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
+  } while (0)
+
+/* first collective after h9_set_soil: every rank learns every rank's cell count and stride
+ * (one small all-gather and one host sync, once), and the persistent buffers are sized */
+int comm_prepare(h9_ctx* ctx) {
+  NcclApi* n = nccl_api();
+  if (!ctx->land_of_rank.empty()) return 0;
+  const int R = ctx->nranks;
+  long long* d_tmp = nullptr;
+  CK(cudaMalloc((void**)&d_tmp, sizeof(long long) * 2 * (size_t)(R + 1)));
+  const long long mine[2] = {(long long)ctx->dev.nc, (long long)ctx->dev.ncs};
+  CK(cudaMemcpyAsync(d_tmp + 2 * R, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  CKN(n->AllGather(d_tmp + 2 * R, d_tmp, 2, ncclInt64, ctx->comm, ctx->stream));
+  std::vector<long long> all(2 * (size_t)R);
+  CK(cudaMemcpyAsync(all.data(), d_tmp, sizeof(long long) * 2 * R, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_tmp);
+  ctx->land_of_rank.resize(R);
+  ctx->stride_of_rank.resize(R);
+  size_t elems = 0;
+  for (int r = 0; r < R; ++r) {
+    ctx->land_of_rank[r] = all[2 * r];
+    ctx->stride_of_rank[r] = all[2 * r + 1];
+    elems += (size_t)kAnnualPlanes * (size_t)all[2 * r + 1];
+  }
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->d_budget_all) cudaFree(ctx->d_budget_all);
+  ctx->d_gather = nullptr;
+  ctx->d_budget_all = nullptr;
+  CK(cudaMalloc((void**)&ctx->d_gather, elems * sizeof(float)));
+  CK(cudaMalloc((void**)&ctx->d_budget_all, (size_t)ctx->nyr * 8 * sizeof(double)));
+  CK(cudaMemsetAsync(ctx->d_budget_all, 0, (size_t)ctx->nyr * 8 * sizeof(double), ctx->stream));
+  ctx->gather_elems = elems;
+  return 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int h9_comm_unique_id(void* id) {
+  if (!id) return H9_ERR_ARG;
+  NcclApi* n = nccl_api();
+  if (!n->lib) {
+    fprintf(stderr, "libh9gpu: cannot load libnccl (%s); set H9_NCCL_LIB\n", n->err.c_str());
+    return H9_ERR_NCCL;
+  }
+  static_assert(sizeof(ncclUniqueId) == H9_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  if (n->GetUniqueId(&u) != ncclSuccess) return H9_ERR_NCCL;
+  memcpy(id, &u, sizeof(u));
+  return H9_OK;
+}
+
+int h9_comm_init(h9_ctx* ctx, int nranks, int rank, const void* id) {
+  if (!ctx) return H9_ERR_ARG;
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id) return fail(ctx, H9_ERR_ARG, "h9_comm_init: bad argument");
+  if (ctx->comm) return fail(ctx, H9_ERR_STATE, "h9_comm_init: communicator already initialised");
+  NcclApi* n = nccl_api();
+  if (!n->lib) return fail(ctx, H9_ERR_NCCL, "h9_comm_init: cannot load libnccl (" + n->err + "); set H9_NCCL_LIB");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  CKN(n->CommInitRank(&ctx->comm, nranks, u, rank));
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  ctx->land_of_rank.clear();
+  ctx->stride_of_rank.clear();
+  return H9_OK;
+}
+
+int h9_comm_destroy(h9_ctx* ctx) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->comm) return H9_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nccl_api()->CommDestroy(ctx->comm);
+  ctx->comm = nullptr;
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->d_budget_all) cudaFree(ctx->d_budget_all);
+  ctx->d_gather = nullptr;
+  ctx->d_budget_all = nullptr;
+  ctx->land_of_rank.clear();
+  ctx->stride_of_rank.clear();
+  ctx->nranks = 1;
+  ctx->rank = 0;
+  return H9_OK;
+}
+
+int h9_comm_land_counts(h9_ctx* ctx, int64_t* n_land) {
+  if (!ctx || !n_land) return H9_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, H9_ERR_STATE, "h9_comm_land_counts: call h9_comm_init first");
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_comm_land_counts: call h9_set_soil first");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  if (comm_prepare(ctx)) return ctx->err.find("nccl") != std::string::npos ? H9_ERR_NCCL : H9_ERR_CUDA;
+  for (int r = 0; r < ctx->nranks; ++r) n_land[r] = ctx->land_of_rank[r];
+  return H9_OK;
+}
+
+int h9_annual_collective(h9_ctx* ctx, int iyr) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, H9_ERR_STATE, "h9_annual_collective: call h9_comm_init first");
+  if (!ctx->have_soil) return fail(ctx, H9_ERR_STATE, "h9_annual_collective: no state");
+  if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_annual_collective: iyr out of range");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  if (comm_prepare(ctx)) return H9_ERR_CUDA;
+  NcclApi* n = nccl_api();
+  /* K5 and both collectives are enqueued on the ctx's stream right behind the stepping
+   * kernel: no host synchronisation, persistent buffers, one budget slot per year */
+  double* slot = ctx->d_budget_all + (size_t)(iyr - 1) * 8;
+  CKL(launch_budget(ctx->stream, ctx->dev, iyr, ctx->d_budget));
+  CKN(n->AllReduce(ctx->d_budget, slot, 8, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  /* ragged all-gather of the 13 annual-mean planes: rank r's [13][ncs_r] block lands at its
+   * offset in every rank's buffer (grouped broadcasts: shards differ in size, no padding) */
+  const float* mine = ctx->dev.annual + (size_t)(iyr - 1) * kAnnualPlanes * ctx->dev.ncs;
+  CKN(n->GroupStart());
+  size_t off = 0;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    const size_t cnt = (size_t)kAnnualPlanes * (size_t)ctx->stride_of_rank[r];
+    ncclResult_t rr = n->Broadcast(r == ctx->rank ? (const void*)mine : (const void*)(ctx->d_gather + off),
+                                   ctx->d_gather + off, cnt, ncclFloat, r, ctx->comm, ctx->stream);
+    if (rr != ncclSuccess) {
+      n->GroupEnd();
+      return fail(ctx, H9_ERR_NCCL, std::string("ncclBroadcast: ") + n->GetErrorString(rr));
+    }
+    off += cnt;
+  }
+  CKN(n->GroupEnd());
+  ctx->gathered_year = iyr;
+  return H9_OK;
+}
+
+int h9_get_gathered_annual(h9_ctx* ctx, int r, float* planes) {
+  if (!ctx || !planes) return H9_ERR_ARG;
+  if (!ctx->comm || ctx->gathered_year < 1) return fail(ctx, H9_ERR_STATE, "h9_get_gathered_annual: no collective has run");
+  if (r < 0 || r >= ctx->nranks) return fail(ctx, H9_ERR_ARG, "h9_get_gathered_annual: bad rank");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  size_t off = 0;
+  for (int q = 0; q < r; ++q) off += (size_t)kAnnualPlanes * (size_t)ctx->stride_of_rank[q];
+  const size_t nl = (size_t)ctx->land_of_rank[r], st = (size_t)ctx->stride_of_rank[r];
+  if (nl == 0) return H9_OK;
+  CK(cudaMemcpy2DAsync(planes, nl * sizeof(float), ctx->d_gather + off, st * sizeof(float),
+                       nl * sizeof(float), kAnnualPlanes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h += (int64_t)(nl * kAnnualPlanes * sizeof(float));
+  return H9_OK;
+}
+
+int h9_get_budget(h9_ctx* ctx, int iyr, double* budget) {
+  if (!ctx || !budget) return H9_ERR_ARG;
+  if (!ctx->comm || !ctx->d_budget_all) return fail(ctx, H9_ERR_STATE, "h9_get_budget: no collective has run");
+  if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_get_budget: iyr out of range");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  CK(cudaMemcpyAsync(budget, ctx->d_budget_all + (size_t)(iyr - 1) * 8, 8 * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h += 64;
+  return H9_OK;
+}
+
+int h9_gathered_device(h9_ctx* ctx, const float** d_planes, const double** d_budget_years) {
+  if (!ctx) return H9_ERR_ARG;
+  if (!ctx->comm || !ctx->d_gather) return fail(ctx, H9_ERR_STATE, "h9_gathered_device: no collective has run");
+  if (d_planes) *d_planes = ctx->d_gather;
+  if (d_budget_years) *d_budget_years = ctx->d_budget_all;
   return H9_OK;
 }
 

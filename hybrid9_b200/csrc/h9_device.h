@@ -86,6 +86,15 @@ struct GrowDiagArrays {
 H9_DECLARE_LAUNCHERS(exact)
 H9_DECLARE_LAUNCHERS(fast)
 
+/* fast mode, two lanes per land cell (h9_kernels_pair.cu): small shards */
+int launch_days_pair(void* stream, const DevArrays& a, const Geo& g, int ndays,
+                     const int32_t* d_year_index, const ForcingView& fv, int cur_year, int nt,
+                     unsigned long long step0, const int32_t* d_cell_index);
+int launch_hydrology_step_pair(void* stream, const DevArrays& a, const Geo& g, const ForcingView& fv,
+                               unsigned long long step0, const StepDiagArrays& diag);
+/* name of the day-kernel instantiation launch_days_fast picks for (nc, block) */
+const char* days_variant_fast(int nc, int block);
+
 /* mode-independent kernels, h9_pack.cu */
 int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes] /* each [ndays][ngrid] */,
                         int ndays, size_t ngrid, const int32_t* d_cell_xy, int nc, int ncs,

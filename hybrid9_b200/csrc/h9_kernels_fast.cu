@@ -9,6 +9,7 @@
  * Compiled for <=128 registers per thread (16 resident warps per SM) by default.
  * K1/K2 are the one-routine entries used by the parity tests.
  */
+#include <cstdlib>
 #include "h9_kernels.cuh"
 #include "h9_physics_fast.cuh"
 
@@ -21,9 +22,20 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
                  int nt, unsigned long long step0, int cells_per_block,
                  const int32_t* __restrict__ cell_index) {
   extern __shared__ float4 smem[];
-  /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells */
-  const int c = blockIdx.x * cells_per_block + threadIdx.x;
-  if (threadIdx.x >= cells_per_block || c >= a.nc) return; /* no barriers below */
+  /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells.
+   * Negative: -lanes, partial warps for small shards -- only the first `lanes` lanes of each
+   * warp hold a cell, so that a shard of a few thousand cells still puts one warp on every
+   * scheduler (the MUFU unit and the issue slot are per scheduler, not per lane) */
+  int c;
+  if (cells_per_block < 0) {
+    const int lanes = -cells_per_block, lane = threadIdx.x & 31;
+    c = (blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) * lanes + lane;
+    if (lane >= lanes) return;
+  } else {
+    c = blockIdx.x * cells_per_block + threadIdx.x;
+    if (threadIdx.x >= cells_per_block) return;
+  }
+  if (c >= a.nc) return; /* no barriers below */
   const CellTable<BLOCK> tbl{smem + threadIdx.x};
 
   FastState s;
@@ -227,14 +239,18 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
   const bool small_shard = (block == 1064) && (a.nc <= nsm * 8 * 32);
   const bool capped = block >= 1000 && !small_shard;
   const int bs = block % 1000;
+  int lanes = 32;
+  if (const char* e = getenv("H9_LANES")) lanes = atoi(e) > 0 && atoi(e) <= 32 ? atoi(e) : 32;
 #define H9_LAUNCH(BS, MINB)                                                                    \
   do {                                                                                         \
     const size_t shm = (size_t)kFastFloatsPerCell * BS * sizeof(float);                        \
     cudaError_t e = cudaFuncSetAttribute(days_kernel_fast<BS, MINB>,                           \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
     if (e != cudaSuccess) return (int)e;                                                       \
-    days_kernel_fast<BS, MINB><<<(a.nc + BS - 1) / BS, BS, shm, st>>>(                         \
-        a, g, ndays, d_year_index, fv, cur_year, nt, step0, BS, d_cell_index);                 \
+    const int cpb = (BS / 32) * lanes;                                                         \
+    days_kernel_fast<BS, MINB><<<(a.nc + cpb - 1) / cpb, BS, shm, st>>>(                       \
+        a, g, ndays, d_year_index, fv, cur_year, nt, step0, lanes == 32 ? BS : -lanes,         \
+        d_cell_index);                                                                         \
   } while (0)
   if (bs == 32) {
     if (capped) H9_LAUNCH(32, 16); else H9_LAUNCH(32, 1);
@@ -245,6 +261,19 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
   }
 #undef H9_LAUNCH
   return (int)cudaGetLastError();
+}
+
+const char* days_variant_fast(int nc, int block) {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (block >= 2000) return "h9::days_kernel_fast<512,1> (balanced)";
+  const bool small_shard = (block == 1064) && (nc <= nsm * 8 * 32);
+  const bool capped = block >= 1000 && !small_shard;
+  const int bs = block % 1000;
+  if (bs == 32) return capped ? "h9::days_kernel_fast<32,16>" : "h9::days_kernel_fast<32,1>";
+  if (bs == 128) return capped ? "h9::days_kernel_fast<128,4>" : "h9::days_kernel_fast<128,1>";
+  return capped ? "h9::days_kernel_fast<64,8>" : "h9::days_kernel_fast<64,1>";
 }
 
 int launch_hydrology_step_fast(void* stream, const DevArrays& a, const Geo& g,

@@ -10,8 +10,11 @@ data-path has no collective at all; per simulated year this module does
     rank that writes axy<yyyy>.nc holds the whole grid, and
   * an FP64 all-reduce of the 8 budget partial sums of h9_annual_device.
 
-Everything here takes torch tensors, so the same code runs over NCCL on the GPUs
-and over gloo on CPU tensors in the tests.
+On the GPUs both collectives run inside libh9gpu (h9_comm_init / h9_annual_collective,
+include/h9gpu.h) on the ctx's own stream; torch.distributed only carries the 128-byte NCCL
+id at start-up, as MPI_Bcast does for the Fortran host.  `gather_annual` is the same
+exchange on torch tensors: the gloo tests use it to cover the host-side logic (padding,
+ragged shards, scatter to the global grid) on CPU.
 """
 from __future__ import annotations
 
@@ -75,14 +78,34 @@ def scatter_to_grid(parts, land_indices, lat_offsets, nx: int, ny: int, fill=np.
     flat = out.reshape(ANNUAL_PLANES, ny * nx)
     for r, p in enumerate(parts):
         idx = np.asarray(land_indices[r], dtype=np.int64) + (int(lat_offsets[r]) - 1) * nx
-        flat[:, idx] = p.detach().cpu().numpy()
+        flat[:, idx] = p if isinstance(p, np.ndarray) else p.detach().cpu().numpy()
     return out
 
 
-def h9_annual_collective(h9, iyr: int, n_land, group=None, device=None):
-    """The per-year collective step for a live H9 context (GPU tensors over NCCL)."""
-    ptr, stride, bptr = h9.annual_device(iyr, budget=True)
-    h9.synchronize()  # budget kernel ran on the ctx stream; NCCL runs on torch's
-    means = device_tensor(ptr, (ANNUAL_PLANES, stride), torch.float32, device)
-    budget = device_tensor(bptr, (BUDGET_LEN,), torch.float64, device)
-    return gather_annual(means, budget, n_land, group)
+def comm_init_from_torch(h9, group=None, device=None):
+    """Bootstrap the library's own NCCL communicator (h9_comm_init) the way the Fortran host
+    does with MPI_Bcast: rank 0 creates the id, the 128 bytes travel over the process group
+    that already exists (NCCL or gloo), every rank joins."""
+    from .host import COMM_ID_BYTES, comm_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = comm_unique_id() if rank == 0 else bytes(COMM_ID_BYTES)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0, group=group)
+    h9.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+    return h9.comm_land_counts()
+
+
+def h9_annual_collective(h9, iyr: int):
+    """The per-year collective step for a live H9 context: one C-ABI call; the budget kernel,
+    the FP64 all-reduce and the all-gather are stream-ordered behind the stepping kernel on the
+    ctx's own stream (no host synchronisation, persistent buffers, one budget slot per year)."""
+    h9.annual_collective(iyr)
+
+
+def fetch_gathered(h9, iyr: int, n_land):
+    """Host copies of what h9_annual_collective left on the device: per-rank compact planes
+    [13, n_land[r]] and the all-reduced budget of year iyr."""
+    parts = [h9.get_gathered_annual(r, int(n)) for r, n in enumerate(n_land)]
+    return parts, h9.get_budget(iyr)

@@ -88,7 +88,29 @@ ABI = {
     "h9_regrid_soil_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [c_f] * 8),
     "h9_partition_lat_bands": (C.c_int, [C.c_int, C.c_int, c_i, c_f, C.c_int, c_i, c_i,
                                          C.POINTER(C.c_int64)]),
+    "h9_kernel_variant": (C.c_char_p, [C.c_void_p]),
+    "h9_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "h9_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "h9_comm_destroy": (C.c_int, [C.c_void_p]),
+    "h9_comm_land_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "h9_annual_collective": (C.c_int, [C.c_void_p, C.c_int]),
+    "h9_get_gathered_annual": (C.c_int, [C.c_void_p, C.c_int, c_f]),
+    "h9_get_budget": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "h9_gathered_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
 }
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """h9_comm_unique_id: rank 0 creates the NCCL id; the host broadcasts these bytes
+    (MPI_Bcast in the Fortran host, torch.distributed / a file in the tests)."""
+    lib = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.h9_comm_unique_id(buf)
+    if rc != 0:
+        raise H9Error(f"h9_comm_unique_id failed ({rc}): libnccl not loadable (set H9_NCCL_LIB)")
+    return buf.raw
 
 
 def library_path() -> str:
@@ -202,6 +224,10 @@ class H9:
     def set_tuning(self, tile_days: int = 0, block: int = 0):
         self._ck(self.lib.h9_set_tuning(self.h, tile_days, block), "h9_set_tuning")
 
+    def kernel_variant(self) -> str:
+        v = self.lib.h9_kernel_variant(self.h)
+        return v.decode() if v else ""
+
     def set_soil(self, soil_tex, theta_s, hksat, bsw, psi_s, fmax):
         s2, s3 = (self.lat_c, self.lon_c), (self.lat_c, self.lon_c, 8)
         _chk32(soil_tex, s2, "soil_tex", np.int32)
@@ -312,6 +338,39 @@ class H9:
         outs = [_f(_chk32(a, coarse, "soil array")) for a in (theta_s, hksat, bsw, psi_s)]
         self._ck(self.lib.h9_regrid_soil_layer(self.h, lon_c, lat_c, layer, *ins, *outs),
                  "h9_regrid_soil_layer")
+
+    # -- multi-GPU: NCCL behind the C ABI ----------------------------------------
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise H9Error("unique_id must be COMM_ID_BYTES long")
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
+        self._ck(self.lib.h9_comm_init(self.h, nranks, rank, buf), "h9_comm_init")
+        self.nranks, self.rank = nranks, rank
+
+    def comm_destroy(self):
+        self._ck(self.lib.h9_comm_destroy(self.h), "h9_comm_destroy")
+
+    def comm_land_counts(self) -> np.ndarray:
+        out = np.zeros(self.nranks, np.int64)
+        self._ck(self.lib.h9_comm_land_counts(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))),
+                 "h9_comm_land_counts")
+        return out
+
+    def annual_collective(self, iyr: int):
+        """Budget kernel + FP64 all-reduce + ragged all-gather of the annual planes, enqueued
+        on the ctx's stream behind the stepping kernel (no host synchronisation)."""
+        self._ck(self.lib.h9_annual_collective(self.h, iyr), "h9_annual_collective")
+
+    def get_gathered_annual(self, r: int, n_land_r: int) -> np.ndarray:
+        out = np.zeros((13, int(n_land_r)), np.float32)
+        self._ck(self.lib.h9_get_gathered_annual(self.h, r, _f(out)), "h9_get_gathered_annual")
+        return out
+
+    def get_budget(self, iyr: int) -> np.ndarray:
+        out = np.zeros(8, np.float64)
+        self._ck(self.lib.h9_get_budget(self.h, iyr, out.ctypes.data_as(C.POINTER(C.c_double))),
+                 "h9_get_budget")
+        return out
 
     # -- faults, sync, counters ---------------------------------------------------
     def get_fault(self) -> H9Fault:

@@ -47,6 +47,7 @@ typedef struct h9_ctx h9_ctx;
 #define H9_ERR_CUDA -2
 #define H9_ERR_STATE -3
 #define H9_ERR_NOMEM -4
+#define H9_ERR_NCCL -5
 
 /* fault bits: the four conditions on which the reference STOPs */
 #define H9_FAULT_TRIDIAG_PIVOT1 1u  /* bmx(1)==0      HYDROLOGY.f90:806-812  */
@@ -55,8 +56,13 @@ typedef struct h9_ctx h9_ctx;
 #define H9_FAULT_WATER_IMBALANCE 8u /* |w1-w0|>0.1    HYDROLOGY.f90:1244-1274 */
 
 /* arithmetic mode of the device kernels */
-#define H9_MATH_EXACT 0 /* IEEE div, no FMA contraction, CUDA powf/expf: follows the Fortran op for op */
-#define H9_MATH_FAST 1  /* FMA contraction, shared reciprocals, in-house positive-domain pow (default) */
+#define H9_MATH_EXACT 0 /* every + - * / is the IEEE operation the Fortran order implies (no FMA
+                         * contraction, IEEE division); pow/exp/log by portable double-precision
+                         * kernels (IEEE double ops + fma only) whose float result is correctly
+                         * rounded: the reference's arithmetic bit for bit, the verification mode */
+#define H9_MATH_FAST 1  /* default: pow(a,b) = ex2.approx(b * lg2.approx(a)), exp by ex2.approx,
+                         * 1/x by rcp.approx (MUFU), explicit FMAs, reciprocals shared and hoisted;
+                         * deviates from EXACT at the FP32 rounding-noise level of the model */
 
 typedef struct h9_fault {
   uint32_t any;       /* OR of the fault bits over all cells since the last clear */
@@ -90,12 +96,24 @@ int h9_set_math(h9_ctx* ctx, int mode);
 #define H9_OPT_REAL_EVAP 1
 int h9_set_option(h9_ctx* ctx, int option, int value);
 
-/* Tuning knobs with no effect on results: days of forcing per pipeline tile of
- * h9_run_days (default 8, env H9_TILE_DAYS) and the launch shape of the
- * time-stepping kernel: threads per block (32, 64 or 128), plus 1000 to select the
- * variant compiled for <=128 registers per thread (16 resident warps per SM, so the
- * 0.5 deg grid runs in one wave).  Default 1064, env H9_BLOCK.  <=0 keeps. */
+/* Tuning knobs: days of forcing per pipeline tile of h9_run_days (default 8, env
+ * H9_TILE_DAYS; no effect on results) and the launch shape of the fast-mode stepping
+ * kernel, `block` (env H9_BLOCK):
+ *   32 / 64 / 128     thread-per-cell kernel, that many threads per block;
+ *   +1000             the same compiled for <=128 registers per thread (16 resident warps per
+ *                     SM, so the 0.5 deg grid runs in one wave);
+ *   4000              the two-lanes-per-cell kernel for small shards (layers 1..4 and 8..5 +
+ *                     aquifer on a lane pair, tridiagonal solved from both ends);
+ *   1064 (default)    automatic: two lanes per cell up to 16 cells x 4 schedulers x SMs
+ *                     (9,472 on a B200; env H9_PAIR_MAX_CELLS overrides), thread per cell with
+ *                     all registers up to 8 warps per SM, the 128-register build above.
+ * All thread-per-cell shapes give the same bits; the two-lanes-per-cell kernel orders the
+ * tridiagonal solve and the column sums differently and agrees with them at rounding level
+ * (FP32 noise floor of the model, tests/test_gpu_pair.py).  A run that must be bit-identical
+ * whatever the shard size (shards == whole grid) pins the shape, e.g. block = 64.  <=0 keeps. */
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block);
+/* name of the stepping-kernel instantiation the next h9_run_days will launch */
+const char* h9_kernel_variant(h9_ctx* ctx);
 
 /* soil_tex (lon_c,lat_c) int32; theta_s,hksat,bsw,psi_s (8,lon_c,lat_c); fmax (lon_c,lat_c).
  * Builds the land mask with the reference's predicate and iteration order
@@ -226,6 +244,34 @@ int h9_regrid_soil_layer(h9_ctx* ctx, int lon_c, int lat_c, int layer, const flo
  * lat_c[r] the row count.  Pure host function, no ctx needed. */
 int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const float* theta_s,
                            int nranks, int32_t* lat_s, int32_t* lat_count, int64_t* n_land);
+
+/* ---- multi-GPU: one ctx per GPU (one per MPI rank), NCCL on the ctx's stream ---------
+ * The reference's ranks exchange nothing during time stepping (HYDROLOGY.f90 indexes only
+ * the current (x,y)) and meet again in the collective netCDF writers
+ * (WRITE_NET_CDF_3DR.f90:93-94,236-257).  These entries give the host the same meeting point
+ * on the device: rank 0 creates an id and broadcasts its H9_COMM_ID_BYTES bytes with the
+ * host's own transport (MPI_Bcast after INIT.f90:26-38), every rank calls h9_comm_init, and
+ * once per simulated year h9_annual_collective enqueues -- on h9_stream(), right behind the
+ * stepping kernel, with no host synchronisation and persistent buffers -- the budget kernel,
+ * an FP64 all-reduce of the 8 budget sums of h9_annual_device into the year's own slot, and
+ * a ragged all-gather of every rank's 13 annual-mean planes.  libnccl is loaded on first use
+ * (dlopen "libnccl.so.2", or the path in env H9_NCCL_LIB); errors return H9_ERR_NCCL. */
+#define H9_COMM_ID_BYTES 128
+int h9_comm_unique_id(void* id /* H9_COMM_ID_BYTES */);
+int h9_comm_init(h9_ctx* ctx, int nranks, int rank, const void* id);
+int h9_comm_destroy(h9_ctx* ctx);
+/* land cells of every rank's block, n_land[nranks] (collective on first use) */
+int h9_comm_land_counts(h9_ctx* ctx, int64_t* n_land);
+/* collective: every rank calls it for the same iyr; asynchronous on h9_stream() */
+int h9_annual_collective(h9_ctx* ctx, int iyr);
+/* results of the last h9_annual_collective (synchronise the stream): rank r's compact
+ * planes [13][n_land[r]] in the order of h9_annual_device, and the all-reduced budget of
+ * year iyr, budget[8] */
+int h9_get_gathered_annual(h9_ctx* ctx, int r, float* planes);
+int h9_get_budget(h9_ctx* ctx, int iyr, double* budget);
+/* device views for stream-ordered consumers: all ranks' planes back to back, rank r's block
+ * [13][stride_r] (stride_r = n_land[r] rounded up to 128); budget slots [nyr][8] */
+int h9_gathered_device(h9_ctx* ctx, const float** d_planes, const double** d_budget_years);
 
 #ifdef __cplusplus
 }

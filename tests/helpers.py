@@ -18,11 +18,19 @@ def make_oracle(world, nisurf=48, nyr=1, kind="f32", loop_order=1, smp_leak=0, n
     return o
 
 
-def make_gpu(world, nisurf=48, nyr=1, mode=0, device=0):
+THREAD_PER_CELL = 64   # h9_set_tuning block: thread-per-cell kernel, 64 threads per block
+TWO_LANES = 4000       # the two-lanes-per-cell kernel (small shards)
+
+
+def make_gpu(world, nisurf=48, nyr=1, mode=0, device=0, block=0):
+    """block: 0 = the library's automatic choice of the fast-mode stepping kernel (two lanes
+    per cell up to ~9.5k cells, thread per cell above), THREAD_PER_CELL / TWO_LANES pin it."""
     from hybrid9_b200 import H9
     h = H9(device)
     h.configure(world.nx, world.ny, nisurf, synth.ZI_DRIVER, nyr=nyr)
     h.set_math(mode)
+    if block:
+        h.set_tuning(0, block)
     h.set_soil(world.soil_tex, world.theta_s, world.hksat, world.bsw, world.psi_s, world.fmax)
     return h
 

@@ -21,7 +21,8 @@ import numpy as np
 import pytest
 
 import oracle_py
-from helpers import (assert_state_close, assert_state_equal, day_slice, make_gpu, make_oracle)
+from helpers import (THREAD_PER_CELL, TWO_LANES, assert_state_close, assert_state_equal, day_slice,
+                     make_gpu, make_oracle)
 from hybrid9_b200 import MATH_EXACT, MATH_FAST, synth
 from hybrid9_b200.state import init_state
 
@@ -189,9 +190,11 @@ def test_exact_vs_oracle_30_days(world, forcing30, which):
 # ---- fast mode vs the oracle, against the rounding-noise floor -----------------------------
 
 
+@pytest.mark.parametrize("block", [THREAD_PER_CELL, TWO_LANES], ids=["thread_per_cell", "two_lanes"])
 @pytest.mark.parametrize("which", ["init", "random"])
-def test_fast_vs_oracle_30_days(world, forcing30, which):
-    """H9_MATH_FAST (MUFU pow/exp/rcp, FMA contraction).  Stated tolerance for 30 days:
+def test_fast_vs_oracle_30_days(world, forcing30, which, block):
+    """H9_MATH_FAST (MUFU pow/exp/rcp, FMA contraction), both stepping kernels (thread per
+    cell; two lanes per cell with the two-sided tridiagonal solve).  Stated tolerance for 30 days:
     median relative error of soil water < 2e-5, 99.9 % within 5e-3, every value within
     5e-2 relative + 0.5 mm, and the worst error no more than 10x the FP32 rounding-noise
     floor measured by the float-vs-double oracle on the same case."""
@@ -206,13 +209,14 @@ def test_fast_vs_oracle_30_days(world, forcing30, which):
         o.set_state(st)
         assert o.run_days(yi, forcing30) == 0
         res[kind] = o.get_state()
-    h = make_gpu(world, mode=MATH_FAST)
+    h = make_gpu(world, mode=MATH_FAST, block=block)
+    assert ("pair" in h.kernel_variant()) == (block == TWO_LANES)
     h.set_state(st)
     assert h.run_days(yi, forcing30) == 0
     got = h.get_state()
     rel = relerr(got.h2osoi_liq[land], res["f32"].h2osoi_liq[land])
     noise = relerr(res["f32"].h2osoi_liq[land], res["f64"].h2osoi_liq[land])
-    record(f"fast_vs_oracle_{which}_30d", h2o_rel_p50=np.median(rel), h2o_rel_p999=np.quantile(rel, 0.999),
+    record(f"fast_vs_oracle_{which}_30d_{'pair' if block == TWO_LANES else 'thread'}", h2o_rel_p50=np.median(rel), h2o_rel_p999=np.quantile(rel, 0.999),
            h2o_rel_max=rel.max(), noise_p50=np.median(noise), noise_p999=np.quantile(noise, 0.999),
            noise_max=noise.max(), zwt_abs_max=np.abs(got.zwt[land] - res["f32"].zwt[land]).max(),
            lai_rel_max=relerr(got.lai[land], res["f32"].lai[land]).max())
@@ -225,7 +229,8 @@ def test_fast_vs_oracle_30_days(world, forcing30, which):
     h.close()
 
 
-def test_fast_single_substep_vs_oracle(world, forcing30):
+@pytest.mark.parametrize("block", [THREAD_PER_CELL, TWO_LANES], ids=["thread_per_cell", "two_lanes"])
+def test_fast_single_substep_vs_oracle(world, forcing30, block):
     """One sub-step from randomised (deliberately extreme) states, fast mode: 99 % of soil
     water within 1e-3 relative, every value within 2e-2 relative + 0.05 mm, and the worst
     error within 10x the float-vs-double rounding noise of the same step."""
@@ -235,7 +240,7 @@ def test_fast_single_substep_vs_oracle(world, forcing30):
     o.set_state(st)
     oo = o.hydrology_step(day_slice(forcing30, 0))
     ref = o.get_state()
-    h = make_gpu(world, mode=MATH_FAST)
+    h = make_gpu(world, mode=MATH_FAST, block=block)
     h.set_state(st)
     go = h.hydrology_step(day_slice(forcing30, 0))
     got = h.get_state()
@@ -245,7 +250,7 @@ def test_fast_single_substep_vs_oracle(world, forcing30):
     ok = land & (np.abs(oo["w_imbalance"]) <= 0.05) & (np.abs(go["w_imbalance"]) <= 0.05)
     rel = relerr(got.h2osoi_liq[ok], ref.h2osoi_liq[ok])
     noise = relerr(ref.h2osoi_liq[ok], o64.get_state().h2osoi_liq[ok])
-    record("fast_single_step", h2o_rel_p50=np.median(rel), h2o_rel_p99=np.quantile(rel, 0.99),
+    record(f"fast_single_step_{'pair' if block == TWO_LANES else 'thread'}", h2o_rel_p50=np.median(rel), h2o_rel_p99=np.quantile(rel, 0.99),
            h2o_rel_max=rel.max(), noise_p99=np.quantile(noise, 0.99), noise_max=noise.max(),
            n_cells=int(ok.sum()), jwt_agree=(go["jwt"][ok] == oo["jwt"][ok]).mean())
     assert np.median(rel) < 1e-5
