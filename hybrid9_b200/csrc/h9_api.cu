@@ -499,6 +499,10 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   d.ncs = std::max(kCellPad, (d.nc + kCellPad - 1) / kCellPad * kCellPad);
   d.nyr = ctx->nyr;
   d.real_evap = ctx->real_evap;
+  {
+    const char* bc = getenv("H9_BUDGET_CELL"); /* read by -DH9_CYCLE_BUDGET builds only */
+    d.budget_cell = bc ? atoi(bc) : 0;
+  }
   const size_t n = (size_t)d.ncs;
   int rc = 0;
   float *ths = nullptr, *hks = nullptr, *bs = nullptr, *ps = nullptr, *fm = nullptr;
@@ -960,8 +964,8 @@ int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const fl
     CKL(launch_hydrology_step_pair(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
                                    ctx->step_counter, diag));
   } else {
-    CKL(launch_hydrology_step_fast(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
-                                   ctx->step_counter, diag));
+    CKL(launch_hydrology_step_fast_variant(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
+                                           ctx->step_counter, diag, ctx->block));
   }
   ctx->step_counter += 1;
   std::vector<float> o;

@@ -56,6 +56,7 @@ struct DevArrays {
   float* first_imb;              /* w1-w0 of that step */
   unsigned long long* first_key; /* min over cells of (step << 32 | cell); ~0 = none */
   uint32_t* any_fault;           /* OR over all cells */
+  int budget_cell;               /* -DH9_CYCLE_BUDGET builds only: the cell whose cycles are recorded */
 };
 
 /* optional per-cell outputs of the fine-grained sub-step entry, compact [ncs] */
@@ -92,6 +93,9 @@ int launch_days_pair(void* stream, const DevArrays& a, const Geo& g, int ndays,
                      unsigned long long step0, const int32_t* d_cell_index);
 int launch_hydrology_step_pair(void* stream, const DevArrays& a, const Geo& g, const ForcingView& fv,
                                unsigned long long step0, const StepDiagArrays& diag);
+int launch_hydrology_step_fast_variant(void* stream, const DevArrays& a, const Geo& g,
+                                       const ForcingView& fv, unsigned long long step0,
+                                       const StepDiagArrays& diag, int block);
 /* name of the day-kernel instantiation launch_days_fast picks for (nc, block) */
 const char* days_variant_fast(int nc, int block);
 

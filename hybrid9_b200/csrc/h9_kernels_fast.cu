@@ -15,6 +15,14 @@
 
 namespace h9 {
 
+#ifdef H9_CYCLE_BUDGET
+/* cycles per segment of cell 0's sub-steps, summed over the launch (tools/cycle_budget.py) */
+__device__ unsigned long long g_cycle_budget[kTickSegs + 2];
+/* per warp of the launch: total cycles of lane 0, and how often its sub-steps took the
+ * cascade / dryness-repair branch */
+__device__ unsigned g_warp_cycles[4096], g_warp_repairs[4096], g_warp_smid[4096];
+#endif
+
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
@@ -56,6 +64,7 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   }
   uint32_t sticky = a.fault[c];
   float evap_sum = a.real_evap ? a.evap_sum[c] : 0.0f;
+  const float evap_on = a.real_evap ? 1.0f : 0.0f;
 
   /* compact forcing [day][7][ncs], or the grid tile as the host holds it gathered through
    * the land index (no separate pack pass on the h9_run_days pipeline) */
@@ -63,6 +72,13 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   Forcing fnext = load_forcing(fv, fcell);
   int iy_next = __ldg(year_index);
 
+#ifdef H9_CYCLE_BUDGET
+  Ticks tk;
+#pragma unroll
+  for (int k = 0; k < kTickSegs; ++k) tk.acc[k] = 0u;
+  unsigned t_loop = 0u, t_all0 = 0u;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(t_all0)::"memory");
+#endif
   for (int d = 0; d < ndays; ++d) {
     const Forcing f = fnext;
     const int iy = iy_next;
@@ -82,12 +98,46 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     float tas;
     day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
 
+    /* fault bookkeeping.  The build with all registers (small shards: one warp per scheduler,
+     * nothing hides the wait for the step's last result) keeps the day's first fault in three
+     * registers and tests once per day; the 128-register build tests every sub-step. */
+    constexpr bool kDeferFault = (MINB == 1);
+    uint32_t ft_day = 0u, ft_first = 0u;
+    int ft_ns = 0;
+    float ft_imb = 0.0f;
     for (int ns = 0; ns < g.nisurf; ++ns) { /* HYBRID9.f90:193-211 */
       StepOut so;
-      const uint32_t ft = hydrology_step_fast(g, tbl, day, s, so);
-      if (ft)
+      /* the build with all registers picks, per warp and sub-step, the step without any
+       * water-table-in-column code when every cell of the warp has a deep table (a uniform
+       * branch), else the general straight-line step; the 128-register build keeps the version
+       * with the fewest instructions */
+      uint32_t ft;
+      if (MINB == 1) {
+        const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
+        ft = all_deep ? hydrology_step_fast<kStepAllDeep>(g, tbl, day, s, so H9_TICKS_ARG)
+                      : hydrology_step_fast<kStepGeneral>(g, tbl, day, s, so H9_TICKS_ARG);
+      } else {
+        ft = hydrology_step_fast<kStepThroughput>(g, tbl, day, s, so H9_TICKS_ARG);
+      }
+      if (kDeferFault) {
+        const bool first = (ft != 0u) && (ft_day == 0u);
+        ft_first = first ? ft : ft_first;
+        ft_ns = first ? ns : ft_ns;
+        ft_imb = first ? so.imbalance : ft_imb;
+        ft_day |= ft;
+      } else if (ft) {
         record_fault(a, c, sticky, ft, step0 + (unsigned long long)d * g.nisurf + ns, so.imbalance);
-      if (a.real_evap) evap_sum += so.qflx_evap_grnd + so.qflx_tran_veg_col; /* H9_OPT_REAL_EVAP */
+      }
+      /* H9_OPT_REAL_EVAP: evap_sum stays 0 otherwise, as in the reference (HYBRID9.f90:137,276) */
+      evap_sum = fmaf(evap_on, so.qflx_evap_grnd + so.qflx_tran_veg_col, evap_sum);
+      H9_TICK(6); /* fault test, loop */
+    }
+    if (kDeferFault && ft_day) {
+      record_fault(a, c, sticky, ft_first, step0 + (unsigned long long)d * g.nisurf + ft_ns, ft_imb);
+      if ((sticky | ft_day) != sticky) { /* further bits raised later in the day */
+        atomicOr(a.any_fault, ft_day);
+        sticky |= ft_day;
+      }
     }
 
     /* GROW (HYBRID9.f90:217): reads smp and rootr, rewrites rootr */
@@ -153,11 +203,36 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   store_grow_state(a, c, gs);
   a.fault[c] = sticky;
   if (a.real_evap) a.evap_sum[c] = evap_sum;
+#ifdef H9_CYCLE_BUDGET
+  unsigned warp_repairs = tk.acc[kTickSegs - 1]; /* most often any lane took the branch */
+  for (int o = 16; o > 0; o >>= 1) warp_repairs = max(warp_repairs, __shfl_xor_sync(__activemask(), warp_repairs, o));
+  if ((threadIdx.x & 31) == 0) {
+    unsigned t_w;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t_w)::"memory");
+    const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    if (wg < 4096) {
+      g_warp_cycles[wg] = t_w - t_all0;
+      g_warp_repairs[wg] = warp_repairs;
+      unsigned smid, warpid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+      g_warp_smid[wg] = (smid << 8) | (warpid & 0xffu);
+    }
+  }
+  if (c == a.budget_cell) {
+    unsigned t_all1;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t_all1)::"memory");
+    for (int k = 0; k < kTickSegs; ++k) g_cycle_budget[k] = tk.acc[k];
+    g_cycle_budget[kTickSegs] = (unsigned long long)(t_all1 - t_all0);
+    g_cycle_budget[kTickSegs + 1] = (unsigned long long)ndays * g.nisurf;
+    (void)t_loop;
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(128)
 hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, const ForcingView fv,
-                           unsigned long long step0, const StepDiagArrays diag) {
+                           unsigned long long step0, const StepDiagArrays diag, int variant) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   float4 col[kFastFloatsPerCell / 4];
@@ -182,7 +257,19 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, con
   float tas;
   day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
   StepOut so;
-  const uint32_t ft = hydrology_step_fast(g, tbl, day, s, so);
+#ifdef H9_CYCLE_BUDGET
+  Ticks tk;
+#endif
+  /* the step variants of the small-shard day kernel, chosen the same way (warp vote) */
+  const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
+  uint32_t ft;
+  if (variant == kStepThroughput) {
+    ft = hydrology_step_fast<kStepThroughput>(g, tbl, day, s, so H9_TICKS_ARG);
+  } else if (all_deep) {
+    ft = hydrology_step_fast<kStepAllDeep>(g, tbl, day, s, so H9_TICKS_ARG);
+  } else {
+    ft = hydrology_step_fast<kStepGeneral>(g, tbl, day, s, so H9_TICKS_ARG);
+  }
   if (ft) record_fault(a, c, sticky, ft, step0, so.imbalance);
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
@@ -276,12 +363,38 @@ const char* days_variant_fast(int nc, int block) {
   return capped ? "h9::days_kernel_fast<64,8>" : "h9::days_kernel_fast<64,1>";
 }
 
+#ifdef H9_CYCLE_BUDGET
+extern "C" int h9_debug_cycle_budget(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_cycle_budget, sizeof(unsigned long long) * (kTickSegs + 2));
+}
+extern "C" int h9_debug_warp_cycles(unsigned* cycles, unsigned* repairs) {
+  cudaError_t e = cudaMemcpyFromSymbol(cycles, g_warp_cycles, sizeof(unsigned) * 4096);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(repairs, g_warp_repairs, sizeof(unsigned) * 4096);
+}
+extern "C" int h9_debug_warp_smid(unsigned* smid) {
+  return (int)cudaMemcpyFromSymbol(smid, g_warp_smid, sizeof(unsigned) * 4096);
+}
+#endif
+
 int launch_hydrology_step_fast(void* stream, const DevArrays& a, const Geo& g,
                                const ForcingView& fv, unsigned long long step0,
                                const StepDiagArrays& diag) {
+  return launch_hydrology_step_fast_variant(stream, a, g, fv, step0, diag, 1064);
+}
+
+/* `block` as for the day kernel: the sub-step variant that kernel would run for this shard */
+int launch_hydrology_step_fast_variant(void* stream, const DevArrays& a, const Geo& g,
+                                       const ForcingView& fv, unsigned long long step0,
+                                       const StepDiagArrays& diag, int block) {
   if (a.nc <= 0) return 0;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const bool small_shard = (block == 1064) && (a.nc <= nsm * 8 * 32);
+  const bool capped = block >= 1000 && block < 2000 && !small_shard;
   hydrology_step_kernel_fast<<<(a.nc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      a, g, fv, step0, diag);
+      a, g, fv, step0, diag, capped ? (int)kStepThroughput : (int)kStepGeneral);
   return (int)cudaGetLastError();
 }
 

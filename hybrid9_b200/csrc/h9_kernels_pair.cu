@@ -67,6 +67,7 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   }
   uint32_t sticky = a.fault[c];
   float evap_sum = a.real_evap ? a.evap_sum[c] : 0.0f;
+  const float evap_on = a.real_evap ? 1.0f : 0.0f;
 
   const size_t fcell = (size_t)(cell_index ? __ldg(cell_index + c) : c);
   Forcing fnext = load_forcing(fv, fcell);
@@ -91,12 +92,32 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     float tas;
     day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
 
+    /* the day's first fault is kept in three registers and recorded once per day: one warp per
+     * scheduler has nothing to hide the wait for the step's last result behind */
+    uint32_t ft_day = 0u, ft_first = 0u;
+    int ft_ns = 0;
+    float ft_imb = 0.0f;
     for (int ns = 0; ns < g.nisurf; ++ns) { /* HYBRID9.f90:193-211 */
       StepOut so;
-      const uint32_t ft = hydrology_step_pair(g, pg, tbl, day, s, so, h, lane);
-      if (ft && writer)
-        record_fault(a, c, sticky, ft, step0 + (unsigned long long)d * g.nisurf + ns, so.imbalance);
-      if (a.real_evap) evap_sum += so.qflx_evap_grnd + so.qflx_tran_veg_col; /* H9_OPT_REAL_EVAP */
+      /* per warp and sub-step: the step without any water-table-in-column code when every cell
+       * of the warp has a deep table (uniform branch), else the general straight-line step */
+      const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
+      const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, pg, tbl, day, s, so, h, lane)
+                                   : hydrology_step_pair<kStepGeneral>(g, pg, tbl, day, s, so, h, lane);
+      const bool first = (ft != 0u) && (ft_day == 0u);
+      ft_first = first ? ft : ft_first;
+      ft_ns = first ? ns : ft_ns;
+      ft_imb = first ? so.imbalance : ft_imb;
+      ft_day |= ft;
+      /* H9_OPT_REAL_EVAP: evap_sum stays 0 otherwise, as in the reference (HYBRID9.f90:137,276) */
+      evap_sum = fmaf(evap_on, so.qflx_evap_grnd + so.qflx_tran_veg_col, evap_sum);
+    }
+    if (ft_day && writer) {
+      record_fault(a, c, sticky, ft_first, step0 + (unsigned long long)d * g.nisurf + ft_ns, ft_imb);
+      if ((sticky | ft_day) != sticky) { /* further bits raised later in the day */
+        atomicOr(a.any_fault, ft_day);
+        sticky |= ft_day;
+      }
     }
 
     /* GROW (HYBRID9.f90:217) on the gathered column: reads smp and rootr, rewrites rootr */
@@ -198,7 +219,9 @@ hydrology_step_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, con
   float tas;
   day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
   StepOut so;
-  const uint32_t ft = hydrology_step_pair(g, pg, tbl, day, s, so, h, lane);
+  const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
+  const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, pg, tbl, day, s, so, h, lane)
+                               : hydrology_step_pair<kStepGeneral>(g, pg, tbl, day, s, so, h, lane);
   if (ft && writer) record_fault(a, c, sticky, ft, step0, so.imbalance);
   float h2o_full[NL];
   pair_gather(s.h2o, h, pmask, h2o_full);

@@ -31,6 +31,42 @@
 
 namespace h9 {
 
+/* Cycle budget of one sub-step (profiles/r02/cycle_budget_*.txt): built only with
+ * -DH9_CYCLE_BUDGET (tools/cycle_budget.py), never in the product library.  H9_TICK(k) closes
+ * segment k: it reads %clock (a scheduling fence: segments no longer overlap, so their sum is
+ * an upper bound of the unfenced sub-step) and adds the cycles since the previous tick. */
+#ifdef H9_CYCLE_BUDGET
+constexpr int kTickSegs = 12;
+struct Ticks {
+  unsigned acc[kTickSegs];
+  unsigned last;
+  __device__ __forceinline__ void start() {
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(last)::"memory");
+  }
+  __device__ __forceinline__ void tick(int k) {
+    unsigned t;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t)::"memory");
+    acc[k] += t - last;
+    last = t;
+  }
+};
+#define H9_TICKS_PARAM , Ticks& tk
+#define H9_TICKS_ARG , tk
+#define H9_TICK(k) tk.tick(k)
+#define H9_TICK_START() tk.start()
+#if H9_CYCLE_BUDGET >= 2 /* coarse: block A is left unfenced inside */
+#define H9_TICK_FINE(k)
+#else
+#define H9_TICK_FINE(k) tk.tick(k)
+#endif
+#else
+#define H9_TICKS_PARAM
+#define H9_TICKS_ARG
+#define H9_TICK(k)
+#define H9_TICK_FINE(k)
+#define H9_TICK_START()
+#endif
+
 /* The per-cell constant table: 27 float4 per cell.  Three groups per soil layer, so that one
  * 128-bit shared-memory load brings the four constants a section of the sub-step needs:
  *   G0 = (psi_s, 1/(-psi_s), 1-1/bsw, psi_s*theta_s/(1-1/bsw)/dz)      equilibrium profile
@@ -150,14 +186,30 @@ __device__ __forceinline__ float fast_specific_yield(const C& c, int i, float zw
   return fmaxf(s_y, 0.02f);
 }
 
-template <class C>
+/* Control flow of the sub-step.  One warp per scheduler (small shards) cannot hide a stall
+ * behind another warp, and ptxas schedules inside basic blocks only, so the step is laid out as
+ * TWO large basic blocks (measured budget: profiles/r02/cycle_budget_*.txt):
+ *   block A  everything up to the end of the forward sweep, branch-free: the serial chains of
+ *            the energy balance and of the aquifer layer run behind the 80 MUFU operations of
+ *            the eight layers (8 cycles each for a lone warp) instead of in front of them;
+ *   block B  the tail, ONE branch on `deep`: a straight-line tail for a water table below the
+ *            column (the common case), the data-dependent Drainage code otherwise; each holds its
+ *            own copy of the back substitution so that it overlaps the water-table chain;
+ *   then     the clamp, the repair trigger as two max/min trees, and the water balance computed
+ *            as if no repair were needed (the rarely taken repair branch redoes it).
+ * Same operations on the same operands as before the re-ordering. */
+enum : int { kStepThroughput = 0, kStepAllDeep = 1, kStepGeneral = 2 };
+
+template <int MODE, class C>
 __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c, const DayFast& d,
-                                                        FastState& s, StepOut& o) {
+                                                        FastState& s, StepOut& o H9_TICKS_PARAM) {
   constexpr float kLog2e = 1.4426950408889634f;
   uint32_t fault = 0;
   const float dt = g.dt, rdt = g.rdt;
   float theta[NL];
+  H9_TICK_START();
 
+  /* ------------------------------ block A ------------------------------ */
   /* :141-151 */
 #pragma unroll
   for (int i = 0; i < NL; ++i) theta[i] = s.h2o[i] * g.rdzw[i + 1];
@@ -179,24 +231,21 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   const float beta = fmaf(rr[0], bw[0], fmaf(rr[1], bw[1], fmaf(rr[2], bw[2], rr[3] * bw[3]))) +
                      fmaf(rr[4], bw[4], fmaf(rr[5], bw[5], fmaf(rr[6], bw[6], rr[7] * bw[7])));
 
-  /* rsc :283-295, rss :325-331 */
+  /* rsc :283-295, rss :325-331 (both branches of rss evaluated, then selected: no jump) */
   float rsc = (d.canopy_on && beta > 0.0f) ? d.rsc_num * MathFast::rcp(d.rsc_den0 * beta) : 1.0E6f;
   rsc = fmaxf(rsc, d.rsc_floor);
-  const float rss = (theta[0] <= 0.15f)
-                        ? d.litter10 * MathFast::ex2((35.63f * kLog2e) * (0.15f - theta[0]))
-                        : fmaf(d.litter1000, 1.0f - theta[0] * c.inv_ths(0), 10.0f);
+  const float rss_dry = d.litter10 * MathFast::ex2((35.63f * kLog2e) * (0.15f - theta[0]));
+  const float rss_wet = fmaf(d.litter1000, 1.0f - theta[0] * c.inv_ths(0), 10.0f);
+  const float rss = (theta[0] <= 0.15f) ? rss_dry : rss_wet;
 
   /* two-source Penman-Monteith :344-389 */
-  /* two reciprocals from one MUFU: 1/a = b/(a*b), 1/b = a/(a*b) (both denominators are
-   * positive and of order 1e-4 .. 1e2) */
   const float dPMc = fmaf(d.gamma, fmaf(rsc, d.inv_raa_rac, 1.0f), d.desatdT);
   const float dPMs = fmaf(d.gamma, fmaf(rss, d.inv_raa_ras, 1.0f), d.desatdT);
   const float Rs = fmaf(d.gamma, rss, d.dg_ras);
   const float Rc = fmaf(d.gamma, rsc, d.dg_rac);
   /* Cc = 1/(1+Rc*Ra/(Rs*(Rc+Ra))) and Cs = 1/(1+Rs*Ra/(Rc*(Rs+Ra))) over the common
-   * denominator Rs*Rc + Rs*Ra + Rc*Ra */
+   * denominator Rs*Rc + Rs*Ra + Rc*Ra; three reciprocals from one MUFU */
   const float RsRc = Rs * Rc, RsRa = Rs * d.Ra, RcRa = Rc * d.Ra;
-  /* three reciprocals from one MUFU */
   const float dD = RsRc + RsRa + RcRa;
   const float pPM = dPMc * dPMs;
   const float r3 = MathFast::rcp(pPM * dD);
@@ -227,13 +276,10 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   const float qflx_infl = qflx_in_soil - qflx_infl_excess;
   qflx_surf += qflx_infl_excess;
 
-  /* SoilWater :492-508 */
+  /* SoilWater :492-508.  jwt == NL  <=>  zwt > zi(8)/1000 (the interfaces increase); the index
+   * itself is only needed by the tail of a cell whose water table is inside the column */
   float zwtmm = 1000.0f * s.zwt;
-  /* jwt == NL  <=>  zwt > zi(8)/1000 (the interfaces increase); the full search only runs for
-   * cells whose water table is inside the column */
   const bool deep = !(s.zwt <= g.zim[NL]);
-  int jwt = NL;
-  if (!deep) jwt = find_jwt(g, s.zwt);
 
   /* equilibrium profile :517-590, branch-free.  With B0 = (-psi+zwtmm-zi(I-1))/(-psi) and
    * BI = (-psi+zwtmm-zi(I))/(-psi), the three cases of the reference are one formula:
@@ -241,11 +287,6 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
    * below the layer both bases are >= 1 and the last term vanishes (:548-558); inside it
    * BI < 1 so the first power is tempi = 1 (:532-540); above it both powers are 1 and
    * (zi(I)-zwtmm)/dz >= 1 so the clamp to theta_s returns theta_s (:523). */
-  /* Layers are processed in pairs and each pair is followed at once by the interface fluxes it
-   * completes and by the rows of the Thomas forward sweep those fluxes complete: the sweep's
-   * dependent chain (one reciprocal per row) then runs behind the powers of the deeper layers
-   * instead of after all of them.  Same operations on the same operands as the separate
-   * loops: the results are bit-identical. */
   float zq[NL + 1];
   float hk[NL], dhkdw[NL], dsmpdw[NL], snode[NL];
   float q[NL], qa[NL], qb[NL]; /* per interface i (below layer i): flux and its two derivatives */
@@ -254,8 +295,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   const float dz9 = deep ? (zwtmm - g.zc[NL]) : g.dz[NL];
   const float4 rc = c.rootr4(0), rd = c.rootr4(1); /* re-read: cheaper than eight live registers */
   const float rs[NL] = {rc.x, rc.y, rc.z, rc.w, rd.x, rd.y, rd.z, rd.w};
-  /* parts of Recharge/Drainage (:856-965) that do not depend on the solve: the aquifer's
-   * specific yield and its reciprocal */
+  /* the aquifer's specific yield and its reciprocal (:925-940): known from the old zwt */
   const float rous_early = fast_specific_yield(c, NL - 1, zwtmm);
   const float rrous_early = MathFast::rcp(rous_early);
 
@@ -299,7 +339,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
   auto row0 = [&]() {
     const float rmx = fmaf(-qflx_tran_veg_col, rs[0], qflx_infl - q[0]);
     bet = g.dzdt[1] + qa[0];
-    if (bet == 0.0f) fault |= FAULT_PIVOT1;
+    fault |= (bet == 0.0f) ? FAULT_PIVOT1 : 0u;
     rbet = MathFast::rcp(bet);
     dwat2[0] = rmx * rbet;
   };
@@ -328,6 +368,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     const float z9 = fmaxf(kSmpmin, psi * fast_pow(fmaxf(vol * c.inv_ths(i), 0.01f), -c.bsw(i)));
     zq[NL] = deep ? z9 : 0.0f;
   }
+  H9_TICK_FINE(0); /* energy balance and the aquifer layer, issued in front of the layers */
 #pragma unroll
   for (int P = 0; P < NL / 2; ++P) {
     eq_layer(2 * P);
@@ -344,6 +385,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
       row(2 * P);
     }
   }
+  H9_TICK_FINE(1); /* eight layers and rows 1-7 */
   { /* aquifer node :645-650 and its interface :737-753; inert when the table is in the column */
     const int i = NL - 1;
     const float b = c.bsw(i), inv_ths = c.inv_ths(i);
@@ -370,123 +412,119 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     minpiv = fminf(minpiv, fabsf(bet));
     dwat2[NL] = fmaf(-amx, dwat2[NL - 1], rmx) * MathFast::rcp(bet);
   }
-  /* for a water table inside the column the Darcy recharge and the specific yield of the
-   * layer holding the table do not depend on the solve either (issued before the back
-   * substitution; they read the NEW smp, :880) */
+  fault |= (minpiv == 0.0f) ? FAULT_PIVOT2 : 0u; /* BET == 0 in some row :818 */
+
+  /* for a step that may hold cells with the water table inside the column: the inputs of
+   * their tail that do not depend on the solve -- the index jwt :499-508 (as a count: the
+   * interfaces increase), the Darcy recharge :866-895 (reads the NEW smp, :880) and the specific
+   * yield of the layer holding the table -- still inside block A, behind the sweep.  Cells
+   * with a deep table compute them on layer 8's constants and drop them. */
+  int jc = NL - 1;
   float qcharge_early = 0.0f, sy_first = 0.02f;
-  if (!deep) {
-    const int jm = (jwt > 1 ? jwt : 1) - 1;
-    const float th_j = pick<NL>(theta, jwt);
-    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
-    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
+  if (MODE == kStepGeneral) {
+    int cnt = 0;
+#pragma unroll
+    for (int I = 1; I <= NL; ++I) cnt += (s.zwt > g.zim[I]) ? 1 : 0;
+    jc = (cnt < NL) ? cnt : NL - 1;
+    const int jm = (jc > 1 ? jc : 1) - 1;
+    const float th_j = pick<NL>(theta, jc);
+    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jc), 0.01f));
+    const float ka = c.hks(jc) * fast_pow(s1, fmaf(2.0f, c.bsw(jc), 3.0f));
     const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
     float zq_j = zq[0];
 #pragma unroll
     for (int k = 1; k < NL; ++k)
       if (jm == k) zq_j = zq[k];
     const float wh = smp1 - zq_j;
-    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jc]) * 2.0f;
     qcharge_early = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
-    sy_first = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
+    sy_first = fast_specific_yield(c, jc, zwtmm); /* layer jwt+1 */
   }
-  if (minpiv == 0.0f) fault |= FAULT_PIVOT2; /* BET == 0 in some row :818 */
-  /* recharge :856-904 */
-  float qcharge;
-  qcharge = deep ? dwat2[NL] * dz9 * rdt : qcharge_early;
-  /* Drainage :923-1009.  The jwt of :923-931 equals the one of :499-508: zwt has not
-   * changed in between */
-  float rous = rous_early;
-  const int jfirst = jwt + 1;
-  if (jwt == NL) {
-    s.wa = fmaf(qcharge, dt, s.wa);
-    s.zwt = fmaf(-(qcharge * dt * 0.001f), rrous_early, s.zwt);
-  } else { /* zwtmm stays the stale value of :492 inside the loops */
-    float qcharge_tot = qcharge * dt;
-    if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
-      for (int I = jwt + 1; I >= 1; --I) {
-        const float s_y = (I == jfirst) ? sy_first : fast_specific_yield(c, I - 1, zwtmm);
-        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
-        s.zwt -= ql * MathFast::rcp(s_y) * 0.001f; /* s_y >= 0.02 > 0 */
-        qcharge_tot -= ql;
-        if (qcharge_tot <= 0.0f) break;
-      }
-    } else { /* deepening, layers jwt+1 .. 8 */
-      for (int I = jwt + 1; I <= NL; ++I) {
-        const float s_y = (I == jfirst) ? sy_first : fast_specific_yield(c, I - 1, zwtmm);
-        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
-        qcharge_tot -= ql;
-        if (qcharge_tot >= 0.0f) {
-          s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
-          break;
-        }
-        s.zwt = g.zim[I];
-      }
-      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
+  H9_TICK(2); /* aquifer node, rows 8-9 */
+
+  /* ------------------------------ block B ------------------------------ */
+  /* back substitution :828-830 and state update :845-850 (only dwat2(9) feeds Recharge and
+   * Drainage, so it is scheduled beside the water-table chain of whichever tail follows) */
+  auto back_substitute = [&]() {
+#pragma unroll
+    for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) s.h2o[i] = fmaf(dwat2[i], g.dz[i + 1], s.h2o[i]);
+  };
+  float rsub_top;
+  int jwt = NL;
+  float zwt_j;
+  float imb, rnf_inc;
+  bool needfix;
+  const float rnf_sum_in = s.rnf_sum;
+  uint32_t fault_bal = 0, fault_tail = 0;
+  /* balance :1221-1244 and the runoff sum :1282-1283 */
+  auto balance = [&](float qflx_rsub_sat) {
+    const float w1 =
+        fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa) +
+        (((s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3])) + ((s.h2o[4] + s.h2o[5]) + (s.h2o[6] + s.h2o[7])));
+    imb = w1 - w0;
+    fault_bal = (!(fabsf(imb) <= 0.1f)) ? FAULT_IMBAL : 0u;
+    const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
+    rnf_inc = r1 + r2;
+    s.rnf_sum = fmaf(rsub_top, dt, fmaf(qflx_surf, dt, rnf_sum_in));
+  };
+  auto excess_tree = [&]() { /* max over the layers of (water - capacity), :1131-1148 */
+    float ov[NL];
+    ov[0] = s.h2o[0] - fmaxf(0.0f, c.ths(0) * g.dz[1]);
+#pragma unroll
+    for (int i = 1; i < NL; ++i) ov[i] = fmaf(-fmaxf(0.01f, c.ths(i)), g.dz[i + 1], s.h2o[i]);
+    return fmaxf(fmaxf(fmaxf(ov[0], ov[1]), fmaxf(ov[2], ov[3])),
+                 fmaxf(fmaxf(ov[4], ov[5]), fmaxf(ov[6], ov[7])));
+  };
+  auto lowest_tree = [&]() {
+    return fminf(fminf(fminf(s.h2o[0], s.h2o[1]), fminf(s.h2o[2], s.h2o[3])),
+                 fminf(fminf(s.h2o[4], s.h2o[5]), fminf(s.h2o[6], s.h2o[7])));
+  };
+  /* End of a tail whose water table is below the column (jwt == NL): clamp :1122-1123, then the
+   * dryness repair :1161-1174 itself, straight line.  Cells of dry regions sit at watmin and
+   * need it EVERY sub-step (transpiration is not limited by the water of the layer, G18), and one
+   * such cell makes its warp pay for a branch: measured 1,970 against 1,530 cycles per sub-step
+   * (profiles/r02/cycle_budget_*.txt).  With jwt == NL the pass never touches zwt (:1166), so it
+   * is seven dependent max/add/sub triples behind the back substitution, in the shadow of the
+   * baseflow chain.  What stays behind the rare branch: the excess cascade :1131-1152 (it comes
+   * first in the reference, so the branch restarts from the saved column) and the upward search
+   * of the bottom layer :1181-1198. */
+  float h_pre[NL];
+  auto finish_deep = [&]() {
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+    const float over = excess_tree();
+#pragma unroll
+    for (int i = 0; i < NL; ++i) h_pre[i] = s.h2o[i];
+#pragma unroll
+    for (int i = 0; i < NL - 1; ++i) {
+      const float xs = fmaxf(kWatmin - s.h2o[i], 0.0f); /* > 0 exactly when h2o < watmin */
+      s.h2o[i] += xs;
+      s.h2o[i + 1] -= xs;
     }
-    jwt = find_jwt(g, s.zwt);
-  }
-
-  zwtmm = 1000.0f * s.zwt; /* :1015 */
-
-  /* baseflow :1024-1118 */
-  float rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
-  rous = fast_specific_yield(c, NL - 1, zwtmm);
-  /* dwat2(9), the only unknown Recharge and Drainage read, is final after the forward sweep;
-   * the back substitution :828-830 and the update of h2osoi_liq :845-850 are issued here,
-   * behind the water-table update and the baseflow's exp / pow, just before baseflow
-   * touches h2osoi_liq */
-#pragma unroll
-  for (int i = NL - 1; i >= 0; --i) dwat2[i] = fmaf(-gam[i + 1], dwat2[i + 1], dwat2[i]);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) s.h2o[i] = fmaf(dwat2[i], g.dz[i + 1], s.h2o[i]);
-  if (jwt == NL) { /* jwt is not recomputed on this path */
-    s.wa = fmaf(-rsub_top, dt, s.wa);
-    s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
-    s.h2o[NL - 1] += fmaxf(0.0f, s.wa - 5000.0f);
-    s.wa = fminf(s.wa, 5000.0f);
-  } else {
-    float rsub_top_tot = -rsub_top * dt;
-    if (rsub_top_tot > 0.0f) {
-      fault |= FAULT_RSUB;
-    } else {
-      for (int I = jwt + 1; I <= NL; ++I) {
-        const float s_y = fast_specific_yield(c, I - 1, zwtmm);
-        const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
-#pragma unroll
-        for (int k = 0; k < NL; ++k)
-          s.h2o[k] = (k == I - 1) ? s.h2o[k] + rl : s.h2o[k]; /* a select, not a jump table */
-        rsub_top_tot -= rl;
-        if (rsub_top_tot >= 0.0f) {
-          s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
-          break;
-        }
-        s.zwt = g.zim[I];
-      }
-      s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* residual, unconditional :1100-1101 */
-      s.wa += rsub_top_tot;
-    }
-    jwt = -1; /* :1110-1116, evaluated from zwt_j only where it is read (dryness repair, output) */
-  }
-  const float zwt_j = s.zwt;
-
-  s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
-
+    needfix = (over > 0.0f || s.h2o[NL - 1] < kWatmin);
+    balance(0.0f);
+  };
+  /* end of a tail in general: clamp, the repair trigger as two max / min trees, and the balance
+   * as if no repair were needed */
+  auto finish = [&]() {
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+    needfix = (excess_tree() > 0.0f || lowest_tree() < kWatmin);
+    balance(0.0f);
+  };
   /* excess cascade :1131-1152 and dryness repair :1161-1205: both are no-ops unless some layer
-   * is above its capacity / below watmin, so ONE rarely taken branch guards them.  The repair's
-   * trigger is taken before the cascade: the cascade only lowers layers to their capacity
-   * (>= 0.01*dz > watmin) and raises others, so it cannot create a layer below watmin, and
-   * inside the branch the repair works from the current values anyway. */
-  float over = s.h2o[0] - fmaxf(0.0f, c.ths(0) * g.dz[1]);
-  float lowest = s.h2o[0];
-#pragma unroll
-  for (int i = 1; i < NL; ++i) {
-    over = fmaxf(over, fmaf(-fmaxf(0.01f, c.ths(i)), g.dz[i + 1], s.h2o[i]));
-    lowest = fminf(lowest, s.h2o[i]);
-  }
-  float qflx_rsub_sat = 0.0f;
-  float xs = 0.0f;
-  if (over > 0.0f || lowest < kWatmin) {
+   * is above its capacity / below watmin, so ONE rarely taken branch guards them (trigger and
+   * water balance were computed in the tail as if no repair were needed; the branch redoes the
+   * balance).  The repair's trigger is taken before the cascade: the cascade only lowers layers
+   * to their capacity (>= 0.01*dz > watmin) and raises others, so it cannot create a layer below
+   * watmin, and inside the branch the repair works from the current values anyway. */
+  auto repair = [&]() {
+#ifdef H9_CYCLE_BUDGET
+    tk.acc[kTickSegs - 1] += 1u; /* how often this thread takes the branch */
+#endif
+    float qflx_rsub_sat = 0.0f;
+    float xs = 0.0f;
 #pragma unroll
     for (int i = NL - 1; i >= 1; --i) {
       const float cap = fmaxf(0.01f, c.ths(i)) * g.dz[i + 1];
@@ -523,27 +561,220 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
         }
       }
     }
+    s.h2o[NL - 1] += xs;  /* :1205 */
+    rsub_top -= xs * rdt; /* :1211 */
+    balance(qflx_rsub_sat);
+  };
+  /* Recharge :896-904, Drainage :946-951 and baseflow :1048-1058 of a water table below the
+   * column, straight-line.  jwt stays NL: it is not recomputed on this path (G10) */
+  auto deep_tail = [&]() {
+    const float qcharge = dwat2[NL] * dz9 * rdt;
+    s.wa = fmaf(qcharge, dt, s.wa);
+    s.zwt = fmaf(-(qcharge * dt * 0.001f), rrous_early, s.zwt);
+    zwtmm = 1000.0f * s.zwt; /* :1015 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
+    const float rous = fast_specific_yield(c, NL - 1, zwtmm);
+    s.wa = fmaf(-rsub_top, dt, s.wa);
+    s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
+    s.h2o[NL - 1] += fmaxf(0.0f, s.wa - 5000.0f);
+    s.wa = fminf(s.wa, 5000.0f);
+    zwt_j = s.zwt;
+  };
+  /* the data-dependent tail of a water table inside the column, as the reference loops it */
+  auto shallow_tail = [&](float qcharge, float sy1) {
+    /* Drainage :953-1009; zwtmm stays the stale value of :492 inside the loops (G9) */
+    const int jfirst = jwt + 1;
+    float qcharge_tot = qcharge * dt;
+    if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
+      for (int I = jwt + 1; I >= 1; --I) {
+        const float s_y = (I == jfirst) ? sy1 : fast_specific_yield(c, I - 1, zwtmm);
+        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
+        s.zwt -= ql * MathFast::rcp(s_y) * 0.001f; /* s_y >= 0.02 > 0 */
+        qcharge_tot -= ql;
+        if (qcharge_tot <= 0.0f) break;
+      }
+    } else { /* deepening, layers jwt+1 .. 8 */
+      for (int I = jwt + 1; I <= NL; ++I) {
+        const float s_y = (I == jfirst) ? sy1 : fast_specific_yield(c, I - 1, zwtmm);
+        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
+        qcharge_tot -= ql;
+        if (qcharge_tot >= 0.0f) {
+          s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
+          break;
+        }
+        s.zwt = g.zim[I];
+      }
+      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
+    }
+    jwt = find_jwt(g, s.zwt);
+    zwtmm = 1000.0f * s.zwt; /* :1015 */
+    /* baseflow :1024-1118 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
+    const float rous = fast_specific_yield(c, NL - 1, zwtmm);
+    if (jwt == NL) { /* the recharge pushed the table below the column */
+      s.wa = fmaf(-rsub_top, dt, s.wa);
+      s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
+      s.h2o[NL - 1] += fmaxf(0.0f, s.wa - 5000.0f);
+      s.wa = fminf(s.wa, 5000.0f);
+    } else {
+      float rsub_top_tot = -rsub_top * dt;
+      if (rsub_top_tot > 0.0f) {
+        fault_tail |= FAULT_RSUB;
+      } else {
+        for (int I = jwt + 1; I <= NL; ++I) {
+          const float s_y = fast_specific_yield(c, I - 1, zwtmm);
+          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
+#pragma unroll
+          for (int k = 0; k < NL; ++k)
+            s.h2o[k] = (k == I - 1) ? s.h2o[k] + rl : s.h2o[k]; /* a select, not a jump table */
+          rsub_top_tot -= rl;
+          if (rsub_top_tot >= 0.0f) {
+            s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
+            break;
+          }
+          s.zwt = g.zim[I];
+        }
+        s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* residual, unconditional :1100-1101 */
+        s.wa += rsub_top_tot;
+      }
+      jwt = -1; /* :1110-1116, evaluated from zwt_j only where it is read (dryness repair, output) */
+    }
+    zwt_j = s.zwt;
+  };
+  /* the Darcy recharge and the first specific yield where block A did not prepare them */
+  auto shallow_inputs = [&](float& qcharge, float& sy1) {
+    jwt = find_jwt(g, s.zwt);
+    const int jm = (jwt > 1 ? jwt : 1) - 1;
+    const float th_j = pick<NL>(theta, jwt);
+    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
+    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
+    const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
+    float zq_j = zq[0];
+#pragma unroll
+    for (int k = 1; k < NL; ++k)
+      if (jm == k) zq_j = zq[k];
+    const float wh = smp1 - zq_j;
+    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    qcharge = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
+    qcharge = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge));
+    sy1 = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
+  };
+
+  if (MODE == kStepThroughput) {
+    /* many warps per scheduler: fewest instructions; one branch on `deep`, the old trigger */
+    if (deep) {
+      back_substitute();
+      deep_tail();
+      finish();
+    } else {
+      float qcharge, sy1;
+      shallow_inputs(qcharge, sy1);
+      back_substitute();
+      shallow_tail(qcharge, sy1);
+      finish();
+    }
+    if (needfix) repair();
+  } else if (MODE == kStepAllDeep) {
+    /* every cell of the warp has its table below the column: no branch but the rare repair */
+    back_substitute();
+    deep_tail();
+    finish_deep();
+    if (needfix) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.h2o[i] = h_pre[i]; /* the cascade comes first */
+      repair();
+    }
+  } else {
+    /* General straight-line tail: the FIRST iteration of each Drainage loop (:961-1009,
+     * :1075-1098) with selects -- almost always the only one -- for cells with the table inside
+     * the column, the deep formulas for the others, one instruction stream for the warp.  A cell
+     * whose loop would go on, or that needs the cascade, the repair with its water-table
+     * move, or the bottom layer's search, restarts the tail from the saved state on the exact
+     * looping code (rare). */
+    back_substitute();
+    const float zwt0 = s.zwt, wa0 = s.wa;
+    float h_bs[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) h_bs[i] = s.h2o[i];
+    const float qcharge = deep ? dwat2[NL] * dz9 * rdt : qcharge_early;
+    const float qtot = qcharge * dt;
+    /* Drainage, first layer (jc = jwt, the layer holding the table) */
+    const bool up = qtot > 0.0f;
+    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - g.zi[jc])), 0.0f);
+    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (g.zi[jc + 1] - zwtmm)), 0.0f);
+    const float ql = up ? ql_up : ql_dn;
+    const float qrem = qtot - ql;
+    const float zmove = zwt0 - ql * MathFast::rcp(sy_first) * 0.001f;
+    const bool done_dn = qrem >= 0.0f;
+    const float zwt1_sh = (up || done_dn) ? zmove : g.zim[jc + 1];
+    const bool more1 = up ? (qrem > 0.0f && jc >= 1) : (!done_dn && jc + 2 <= NL);
+    const float zwt1 = deep ? fmaf(-(qcharge * dt * 0.001f), rrous_early, zwt0) : zwt1_sh;
+    const float wa1 = deep ? fmaf(qcharge, dt, wa0) : wa0;
+    /* baseflow, first layer below the new table */
+    const float zwtmm1 = 1000.0f * zwt1; /* :1015 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * zwt1);
+    const float rous = fast_specific_yield(c, NL - 1, zwtmm1);
+    const float rrous = MathFast::rcp(rous);
+    int cnt2 = 0;
+#pragma unroll
+    for (int I = 1; I <= NL; ++I) cnt2 += (zwt1 > g.zim[I]) ? 1 : 0;
+    const bool isA = deep || cnt2 == NL; /* table below the column: :1048-1058 */
+    const int j2c = (cnt2 < NL) ? cnt2 : NL - 1;
+    const float sy2 = fast_specific_yield(c, j2c, zwtmm1);
+    const float rtot = -rsub_top * dt;
+    const float rl = fminf(fmaxf(rtot, -(sy2 * (g.zi[j2c + 1] - zwtmm1))), 0.0f);
+    const float rrem = rtot - rl;
+    const bool done2 = rrem >= 0.0f;
+    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : g.zim[j2c + 1];
+    const bool more2 = !isA && ((!done2 && j2c + 2 <= NL) || rtot > 0.0f);
+    const float zwt_c = zwt_b - rrem * 0.001f * rrous; /* residual, unconditional :1100-1101 */
+    const float wa_c = wa1 + rrem;
+    const float wa_a = fmaf(-rsub_top, dt, wa1);
+    const float zwt_a = fmaf(rsub_top * dt * 0.001f, rrous, zwt1);
+    zwt_j = isA ? zwt_a : zwt_c;
+    jwt = isA ? NL : -1; /* :1110-1116 only where it is read (the output of the one-step entry) */
+    const float wa2 = isA ? wa_a : wa_c;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) s.h2o[k] = (!isA && k == j2c) ? s.h2o[k] + rl : s.h2o[k];
+    s.h2o[NL - 1] += isA ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
+    s.wa = isA ? fminf(wa2, 5000.0f) : wa2;
+    /* clamp, triggers, the dryness pass where it cannot move the table, balance */
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+    const float over = excess_tree();
+    const float lowest = lowest_tree();
+#pragma unroll
+    for (int i = 0; i < NL - 1; ++i) {
+      const float xs = isA ? fmaxf(kWatmin - s.h2o[i], 0.0f) : 0.0f;
+      s.h2o[i] += xs;
+      s.h2o[i + 1] -= xs;
+    }
+    const bool fix = over > 0.0f || (isA ? (s.h2o[NL - 1] < kWatmin) : (lowest < kWatmin));
+    balance(0.0f);
+    if ((more1 && !deep) || more2 || fix) { /* rare: the exact looping code from the saved state */
+      s.zwt = zwt0;
+      s.wa = wa0;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.h2o[i] = h_bs[i];
+      zwtmm = 1000.0f * zwt0;
+      if (deep) {
+        deep_tail();
+      } else {
+        jwt = jc;
+        shallow_tail(qcharge_early, sy_first);
+      }
+      finish();
+      if (needfix) repair();
+    }
   }
-  s.h2o[NL - 1] += xs;  /* :1205 */
-  rsub_top -= xs * rdt; /* :1211 */
-
-  /* balance :1221-1244 */
-  const float w1 =
-      fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa) +
-      (((s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3])) + ((s.h2o[4] + s.h2o[5]) + (s.h2o[6] + s.h2o[7])));
-  const float imb = w1 - w0;
-  if (!(fabsf(imb) <= 0.1f)) fault |= FAULT_IMBAL;
-
-  /* :1282-1283 */
-  const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
-  s.rnf_sum = fmaf(rsub_top, dt, fmaf(qflx_surf, dt, s.rnf_sum));
+  fault |= fault_tail;
+  H9_TICK(3); /* tail: recharge, drainage, baseflow, back substitution, trigger, balance, rare repair */
 
   o.qflx_tran_veg_col = qflx_tran_veg_col;
   o.qflx_evap_grnd = qflx_evap_grnd;
-  o.rnf_inc = r1 + r2;
+  o.rnf_inc = rnf_inc;
   o.imbalance = imb;
   o.jwt = (jwt < 0) ? find_jwt(g, zwt_j) : jwt; /* dead code where the caller ignores it (K3) */
-  return fault;
+  return fault | fault_bal;
 }
 
 } /* namespace h9 */

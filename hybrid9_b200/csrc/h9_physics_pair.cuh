@@ -178,7 +178,10 @@ __device__ __forceinline__ float pair_specific_yield(const C& c, int i, float zw
   return fmaxf(s_y, 0.02f);
 }
 
-template <class C>
+/* Control flow as in hydrology_step_fast (h9_physics_fast.cuh): block A is one basic block up
+ * to the junction solve; MODE kStepAllDeep has a straight-line tail, kStepGeneral the
+ * first-iteration-with-selects tail and the rare restart on the looping code. */
+template <int MODE, class C>
 __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const PairGeo& pg, const C& c,
                                                         const DayFast& d, PairState& s, StepOut& o,
                                                         const int h, const int lane) {
@@ -188,6 +191,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
   const float dt = g.dt, rdt = g.rdt;
   const bool odd = (h != 0);
 
+  /* ------------------------------ block A ------------------------------ */
   /* :141-151 */
   float theta[NH];
 #pragma unroll
@@ -218,9 +222,9 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
   /* rsc :283-295, rss :325-331 */
   float rsc = (d.canopy_on && beta > 0.0f) ? d.rsc_num * MathFast::rcp(d.rsc_den0 * beta) : 1.0E6f;
   rsc = fmaxf(rsc, d.rsc_floor);
-  const float rss = (th_top <= 0.15f)
-                        ? d.litter10 * MathFast::ex2((35.63f * kLog2e) * (0.15f - th_top))
-                        : fmaf(d.litter1000, 1.0f - th_top * mi.w, 10.0f);
+  const float rss_dry = d.litter10 * MathFast::ex2((35.63f * kLog2e) * (0.15f - th_top));
+  const float rss_wet = fmaf(d.litter1000, 1.0f - th_top * mi.w, 10.0f);
+  const float rss = (th_top <= 0.15f) ? rss_dry : rss_wet;
 
   /* two-source Penman-Monteith :344-389 (as in h9_physics_fast.cuh) */
   const float dPMc = fmaf(d.gamma, fmaf(rsc, d.inv_raa_rac, 1.0f), d.desatdT);
@@ -260,8 +264,6 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
   /* SoilWater :492-508 */
   float zwtmm = 1000.0f * s.zwt;
   const bool deep = !(s.zwt <= g.zim[NL]);
-  int jwt = NL;
-  if (!deep) jwt = find_jwt(g, s.zwt);
   const float dz9 = deep ? (zwtmm - g.zc[NL]) : g.dz[NL];
   const float rous_early = pair_specific_yield(c, NL - 1, zwtmm);
   const float rrous_early = MathFast::rcp(rous_early);
@@ -275,6 +277,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
   for (int k = 0; k < NH - 1; ++k) tsum[k + 1] = theta[k] + theta[k + 1];
   tsum[NH] = theta[NH - 1] + pth3;
 
+  float rden_m1;
   { /* outer node of the odd lane: the aquifer layer :576-590 and node :645-650 (the even
      * lane runs the same instructions on its top layer's constants; the result is unused) */
     const float4 A = c.g0(0), B = c.g1(0);
@@ -294,10 +297,8 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     const float den9 = zc9 - g.zc[NL];
     const float r9 = MathFast::rcp(s_node * den9);
     dsm[0] = B.w * smpn[0] * (r9 * den9);
-    /* 1/(zc(9)-zc(8)) of interface -1 */
-    snode[0] = r9 * s_node; /* parked here until the flux below reads it */
+    rden_m1 = r9 * s_node; /* 1/(zc(9)-zc(8)) of interface -1 */
   }
-  const float rden_m1 = snode[0];
 
 #pragma unroll
   for (int j = 0; j < NH; ++j) { /* equilibrium profile :517-573 and matric potential :626-639 */
@@ -364,7 +365,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     const float rmx = fmaf(-qflx_tran_veg_col, rr[0], Fm1 - F[1]);
     const float dg = (pg.dzdt[0] - Fbm1) + Fa[1];
     const float bet = fmaf(Fam1, gam[0], dg);
-    if (!odd && bet == 0.0f) fault |= FAULT_PIVOT1; /* bmx(1) == 0 :806 */
+    fault |= (!odd && bet == 0.0f) ? FAULT_PIVOT1 : 0u; /* bmx(1) == 0 :806 */
     minpiv = fminf(minpiv, fabsf(bet));
     rbet = MathFast::rcp(bet);
     u[1] = fmaf(Fam1, u[0], rmx) * rbet;
@@ -392,119 +393,95 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
 #pragma unroll
   for (int j = NH - 1; j >= 0; --j) dw[j] = fmaf(-gam[j], dw[j + 1], u[j]);
   const float dwat9 = __shfl_sync(kFullMask, dw[0], lane | 1); /* dwat2(9), held by the odd lane */
-  if (minpiv == 0.0f) fault |= FAULT_PIVOT2;
+  fault |= (minpiv == 0.0f) ? FAULT_PIVOT2 : 0u;
 
-  /* recharge for a water table inside the column :866-895 (reads the NEW smp, :880) */
+  /* inputs of the tail of a cell whose table is inside the column that do not depend on the
+   * solve (see hydrology_step_fast): jwt as a count, the Darcy recharge :866-895, the first
+   * specific yield.  The warp is converged here: full-mask shuffles. */
+  int jc = NL - 1;
   float qcharge_early = 0.0f, sy_first = 0.02f;
-  if (!deep) {
-    const int jm = (jwt > 1 ? jwt : 1) - 1;
-    const float th_j = pair_fetch(theta, jwt, pmask, lane);
+  if (MODE == kStepGeneral) {
+    int cnt = 0;
+#pragma unroll
+    for (int I = 1; I <= NL; ++I) cnt += (s.zwt > g.zim[I]) ? 1 : 0;
+    jc = (cnt < NL) ? cnt : NL - 1;
+    const int jm = (jc > 1 ? jc : 1) - 1;
     float smp_own[NH], zq_own[NH];
 #pragma unroll
     for (int j = 0; j < NH; ++j) {
       smp_own[j] = s.smp[j];
       zq_own[j] = zq[1 + j];
     }
-    const float smp1 = fmaxf(kSmpmin, pair_fetch(smp_own, jm, pmask, lane));
-    const float zq_j = pair_fetch(zq_own, jm, pmask, lane);
-    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
-    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
+    const float th_j = pair_fetch(theta, jc, kFullMask, lane);
+    const float smp1 = fmaxf(kSmpmin, pair_fetch(smp_own, jm, kFullMask, lane));
+    const float zq_j = pair_fetch(zq_own, jm, kFullMask, lane);
+    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jc), 0.01f));
+    const float ka = c.hks(jc) * fast_pow(s1, fmaf(2.0f, c.bsw(jc), 3.0f));
     const float wh = smp1 - zq_j;
-    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jc]) * 2.0f;
     qcharge_early = ka * wh * MathFast::rcp(denom);
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
-    sy_first = pair_specific_yield(c, jwt, zwtmm);
-  }
-  const float qcharge = deep ? dwat9 * dz9 * rdt : qcharge_early;
-
-  /* Drainage :923-1009 */
-  const int jfirst = jwt + 1;
-  if (jwt == NL) {
-    s.wa = fmaf(qcharge, dt, s.wa);
-    s.zwt = fmaf(-(qcharge * dt * 0.001f), rrous_early, s.zwt);
-  } else { /* zwtmm stays the stale value of :492 inside the loops (G9) */
-    float qcharge_tot = qcharge * dt;
-    if (qcharge_tot > 0.0f) {
-      for (int I = jwt + 1; I >= 1; --I) {
-        const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
-        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
-        s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
-        qcharge_tot -= ql;
-        if (qcharge_tot <= 0.0f) break;
-      }
-    } else {
-      for (int I = jwt + 1; I <= NL; ++I) {
-        const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
-        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
-        qcharge_tot -= ql;
-        if (qcharge_tot >= 0.0f) {
-          s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
-          break;
-        }
-        s.zwt = g.zim[I];
-      }
-      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
-    }
-    jwt = find_jwt(g, s.zwt);
+    sy_first = pair_specific_yield(c, jc, zwtmm);
   }
 
-  zwtmm = 1000.0f * s.zwt; /* :1015 */
-
-  /* baseflow :1024-1118 */
-  float rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
-  const float rous = pair_specific_yield(c, NL - 1, zwtmm);
+  /* ------------------------------ block B ------------------------------ */
   /* state update :845-850 */
 #pragma unroll
   for (int j = 0; j < NH; ++j) s.h2o[j] = fmaf(dw[j + 1], pg.dz[j], s.h2o[j]);
-  if (jwt == NL) { /* jwt is not recomputed on this path (G10) */
-    s.wa = fmaf(-rsub_top, dt, s.wa);
-    s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
-    s.h2o[0] += odd ? fmaxf(0.0f, s.wa - 5000.0f) : 0.0f; /* layer 8 is the odd lane's j = 0 */
-    s.wa = fminf(s.wa, 5000.0f);
-  } else {
-    float rsub_top_tot = -rsub_top * dt;
-    if (rsub_top_tot > 0.0f) {
-      fault |= FAULT_RSUB;
-    } else {
-      for (int I = jwt + 1; I <= NL; ++I) {
-        const float s_y = pair_specific_yield(c, I - 1, zwtmm);
-        const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
-        const int jl = (I - 1 < NH) ? I - 1 : NL - I;     /* local index of layer I */
-        const bool mine = ((I - 1 >= NH) == odd);
-#pragma unroll
-        for (int k = 0; k < NH; ++k) s.h2o[k] = (mine && k == jl) ? s.h2o[k] + rl : s.h2o[k];
-        rsub_top_tot -= rl;
-        if (rsub_top_tot >= 0.0f) {
-          s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
-          break;
-        }
-        s.zwt = g.zim[I];
-      }
-      s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* :1100-1101, unconditional (G11) */
-      s.wa += rsub_top_tot;
-    }
-    jwt = -1;
-  }
-  const float zwt_j = s.zwt;
-  s.zwt = fminf(80.0f, fmaxf(0.0f, s.zwt)); /* :1122-1123 */
 
-  /* excess cascade :1131-1152 and dryness repair :1161-1205: rarely needed; the trigger and
-   * the fault word of the two lanes are merged with one shuffle */
+  float rsub_top;
+  int jwt = NL;
+  float zwt_j;
+  float imb = 0.0f, rnf_inc = 0.0f;
+  const float rnf_sum_in = s.rnf_sum;
+  uint32_t fault_bal = 0, fault_tail = 0;
   const float4 capv = c.cap();
   const float cp[NH] = {capv.x, capv.y, capv.z, capv.w};
-  float over = s.h2o[0] - cp[0], lowest = s.h2o[0];
+  /* balance :1221-1244 and the runoff sum :1282-1283; the column sum crosses the pair */
+  auto balance = [&](float qflx_rsub_sat, unsigned mask) {
+    const float wl1 = (s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3]);
+    const float w1 =
+        fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa) +
+        (wl1 + __shfl_xor_sync(mask, wl1, 1));
+    imb = w1 - w0;
+    fault_bal = (!(fabsf(imb) <= 0.1f)) ? FAULT_IMBAL : 0u;
+    const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
+    rnf_inc = r1 + r2;
+    s.rnf_sum = fmaf(rsub_top, dt, fmaf(qflx_surf, dt, rnf_sum_in));
+  };
+  auto excess_local = [&]() { /* max over the lane's layers of (water - capacity), :1131-1148 */
+    return fmaxf(fmaxf(s.h2o[0] - cp[0], s.h2o[1] - cp[1]), fmaxf(s.h2o[2] - cp[2], s.h2o[3] - cp[3]));
+  };
+  auto lowest_local = [&]() {
+    return fminf(fminf(s.h2o[0], s.h2o[1]), fminf(s.h2o[2], s.h2o[3]));
+  };
+  /* the dryness repair :1161-1174 for a table below the column (it cannot move zwt, :1166),
+   * straight-line over the pair: layers 1..4 top-down in the even lane, the deficit of layer 4
+   * handed across the junction, layers 5..7 in the odd lane (its local order is bottom-up);
+   * `on` masks it per cell */
+  auto dryness_pass = [&](bool on) {
+    const bool ev = on && !odd, od = on && odd;
 #pragma unroll
-  for (int j = 1; j < NH; ++j) {
-    over = fmaxf(over, s.h2o[j] - cp[j]);
-    lowest = fminf(lowest, s.h2o[j]);
-  }
-  uint32_t flags = fault | ((over > 0.0f || lowest < kWatmin) ? 0x100u : 0u);
-  flags |= __shfl_xor_sync(kFullMask, flags, 1);
-  fault = flags & 0xFFu;
-  float qflx_rsub_sat = 0.0f;
-  float xs = 0.0f;
-  if (flags & 0x100u) { /* both lanes of the pair take it together: gather the column, repair
-                         * it sequentially as the reference does, keep the own half */
+    for (int j = 0; j < NH - 1; ++j) {
+      const float xs = ev ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
+      s.h2o[j] += xs;
+      s.h2o[j + 1] -= xs;
+    }
+    const float xs3 = ev ? fmaxf(kWatmin - s.h2o[NH - 1], 0.0f) : 0.0f;
+    s.h2o[NH - 1] += xs3;
+    const float pxs3 = pair_xor(xs3);
+    s.h2o[NH - 1] -= od ? pxs3 : 0.0f; /* layer 5 gives to layer 4 */
+#pragma unroll
+    for (int j = NH - 1; j >= 1; --j) {
+      const float xs = od ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
+      s.h2o[j] += xs;
+      s.h2o[j - 1] -= xs;
+    }
+  };
+  /* excess cascade :1131-1152 and dryness repair :1161-1205 as the reference orders them, on
+   * the gathered column; both lanes of the pair take the branch together */
+  auto repair = [&]() {
+    float qflx_rsub_sat = 0.0f, xs = 0.0f;
     float w[NL];
     pair_gather(s.h2o, h, pmask, w);
 #pragma unroll
@@ -545,27 +522,189 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     w[NL - 1] += xs; /* :1205 */
 #pragma unroll
     for (int j = 0; j < NH; ++j) s.h2o[j] = odd ? w[NL - 1 - j] : w[j];
+    rsub_top -= xs * rdt; /* :1211 */
+    balance(qflx_rsub_sat, pmask);
+  };
+  /* Recharge :896-904, Drainage :946-951, baseflow :1048-1058 for a table below the column */
+  auto deep_tail = [&]() {
+    const float qcharge = dwat9 * dz9 * rdt;
+    s.wa = fmaf(qcharge, dt, s.wa);
+    s.zwt = fmaf(-(qcharge * dt * 0.001f), rrous_early, s.zwt);
+    zwtmm = 1000.0f * s.zwt; /* :1015 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
+    const float rous = pair_specific_yield(c, NL - 1, zwtmm);
+    s.wa = fmaf(-rsub_top, dt, s.wa);
+    s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
+    s.h2o[0] += odd ? fmaxf(0.0f, s.wa - 5000.0f) : 0.0f; /* layer 8 is the odd lane's j = 0 */
+    s.wa = fminf(s.wa, 5000.0f);
+    zwt_j = s.zwt;
+  };
+  /* the data-dependent tail of a table inside the column, as the reference loops it */
+  auto shallow_tail = [&]() {
+    const int jfirst = jwt + 1;
+    float qcharge_tot = qcharge_early * dt;
+    if (qcharge_tot > 0.0f) {
+      for (int I = jwt + 1; I >= 1; --I) {
+        const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
+        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
+        s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
+        qcharge_tot -= ql;
+        if (qcharge_tot <= 0.0f) break;
+      }
+    } else {
+      for (int I = jwt + 1; I <= NL; ++I) {
+        const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
+        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
+        qcharge_tot -= ql;
+        if (qcharge_tot >= 0.0f) {
+          s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
+          break;
+        }
+        s.zwt = g.zim[I];
+      }
+      if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
+    }
+    jwt = find_jwt(g, s.zwt);
+    zwtmm = 1000.0f * s.zwt; /* :1015 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * s.zwt);
+    const float rous = pair_specific_yield(c, NL - 1, zwtmm);
+    if (jwt == NL) {
+      s.wa = fmaf(-rsub_top, dt, s.wa);
+      s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
+      s.h2o[0] += odd ? fmaxf(0.0f, s.wa - 5000.0f) : 0.0f;
+      s.wa = fminf(s.wa, 5000.0f);
+    } else {
+      float rsub_top_tot = -rsub_top * dt;
+      if (rsub_top_tot > 0.0f) {
+        fault_tail |= FAULT_RSUB;
+      } else {
+        for (int I = jwt + 1; I <= NL; ++I) {
+          const float s_y = pair_specific_yield(c, I - 1, zwtmm);
+          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
+          const int jl = (I - 1 < NH) ? I - 1 : NL - I; /* local index of layer I */
+          const bool mine = ((I - 1 >= NH) == odd);
+#pragma unroll
+          for (int k = 0; k < NH; ++k) s.h2o[k] = (mine && k == jl) ? s.h2o[k] + rl : s.h2o[k];
+          rsub_top_tot -= rl;
+          if (rsub_top_tot >= 0.0f) {
+            s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
+            break;
+          }
+          s.zwt = g.zim[I];
+        }
+        s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* :1100-1101, unconditional (G11) */
+        s.wa += rsub_top_tot;
+      }
+      jwt = -1;
+    }
+    zwt_j = s.zwt;
+  };
+  /* merge the pair's trigger and fault bits: one shuffle */
+  auto merge_flags = [&](bool fix_local, unsigned mask) {
+    uint32_t flags = fault | fault_tail | (fix_local ? 0x100u : 0u);
+    flags |= __shfl_xor_sync(mask, flags, 1);
+    fault = flags & 0xFFu;
+    return (flags & 0x100u) != 0u;
+  };
+
+  if (MODE == kStepAllDeep) {
+    deep_tail();
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j)); /* :1122-1123 */
+    const float over = excess_local();
+    float h_pre[NH];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) h_pre[j] = s.h2o[j];
+    dryness_pass(true);
+    balance(0.0f, kFullMask);
+    /* layer 8 (the odd lane's j = 0) is not reached by the pass: :1181-1198 is in the branch */
+    if (merge_flags(over > 0.0f || (odd && s.h2o[0] < kWatmin), kFullMask)) {
+#pragma unroll
+      for (int j = 0; j < NH; ++j) s.h2o[j] = h_pre[j]; /* the cascade comes first */
+      repair();
+    }
+  } else {
+    /* general straight-line tail, see hydrology_step_fast */
+    const float zwt0 = s.zwt, wa0 = s.wa;
+    float h_bs[NH];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) h_bs[j] = s.h2o[j];
+    const float qcharge = deep ? dwat9 * dz9 * rdt : qcharge_early;
+    const float qtot = qcharge * dt;
+    const bool up = qtot > 0.0f;
+    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - g.zi[jc])), 0.0f);
+    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (g.zi[jc + 1] - zwtmm)), 0.0f);
+    const float ql = up ? ql_up : ql_dn;
+    const float qrem = qtot - ql;
+    const float zmove = zwt0 - ql * MathFast::rcp(sy_first) * 0.001f;
+    const bool done_dn = qrem >= 0.0f;
+    const float zwt1_sh = (up || done_dn) ? zmove : g.zim[jc + 1];
+    const bool more1 = up ? (qrem > 0.0f && jc >= 1) : (!done_dn && jc + 2 <= NL);
+    const float zwt1 = deep ? fmaf(-(qcharge * dt * 0.001f), rrous_early, zwt0) : zwt1_sh;
+    const float wa1 = deep ? fmaf(qcharge, dt, wa0) : wa0;
+    const float zwtmm1 = 1000.0f * zwt1; /* :1015 */
+    rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * zwt1);
+    const float rous = pair_specific_yield(c, NL - 1, zwtmm1);
+    const float rrous = MathFast::rcp(rous);
+    int cnt2 = 0;
+#pragma unroll
+    for (int I = 1; I <= NL; ++I) cnt2 += (zwt1 > g.zim[I]) ? 1 : 0;
+    const bool isA = deep || cnt2 == NL;
+    const int j2c = (cnt2 < NL) ? cnt2 : NL - 1;
+    const float sy2 = pair_specific_yield(c, j2c, zwtmm1);
+    const float rtot = -rsub_top * dt;
+    const float rl = fminf(fmaxf(rtot, -(sy2 * (g.zi[j2c + 1] - zwtmm1))), 0.0f);
+    const float rrem = rtot - rl;
+    const bool done2 = rrem >= 0.0f;
+    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : g.zim[j2c + 1];
+    const bool more2 = !isA && ((!done2 && j2c + 2 <= NL) || rtot > 0.0f);
+    const float zwt_c = zwt_b - rrem * 0.001f * rrous;
+    const float wa_c = wa1 + rrem;
+    const float wa_a = fmaf(-rsub_top, dt, wa1);
+    const float zwt_a = fmaf(rsub_top * dt * 0.001f, rrous, zwt1);
+    zwt_j = isA ? zwt_a : zwt_c;
+    jwt = isA ? NL : -1;
+    const float wa2 = isA ? wa_a : wa_c;
+    {
+      const int jl = (j2c < NH) ? j2c : NL - 1 - j2c; /* local index of layer j2c+1 */
+      const bool mine = !isA && ((j2c >= NH) == odd);
+#pragma unroll
+      for (int k = 0; k < NH; ++k) s.h2o[k] = (mine && k == jl) ? s.h2o[k] + rl : s.h2o[k];
+    }
+    s.h2o[0] += (isA && odd) ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
+    s.wa = isA ? fminf(wa2, 5000.0f) : wa2;
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+    const float over = excess_local();
+    const float lowest = lowest_local();
+    dryness_pass(isA);
+    balance(0.0f, kFullMask);
+    const bool fix_local = (more1 && !deep) || more2 || over > 0.0f ||
+                           (isA ? (odd && s.h2o[0] < kWatmin) : (lowest < kWatmin));
+    if (merge_flags(fix_local, kFullMask)) { /* rare: the looping code from the saved state */
+      s.zwt = zwt0;
+      s.wa = wa0;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) s.h2o[j] = h_bs[j];
+      zwtmm = 1000.0f * zwt0;
+      if (deep) {
+        deep_tail();
+      } else {
+        jwt = jc;
+        shallow_tail();
+      }
+      s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+      fault |= fault_tail;
+      const bool fix2 = merge_flags(excess_local() > 0.0f || lowest_local() < kWatmin, pmask);
+      balance(0.0f, pmask);
+      if (fix2) repair();
+    }
   }
-  rsub_top -= xs * rdt; /* :1211 */
-
-  /* balance :1221-1244 */
-  const float wl1 = (s.h2o[0] + s.h2o[1]) + (s.h2o[2] + s.h2o[3]);
-  const float w1 =
-      fmaf((qflx_surf + qflx_evap_grnd + qflx_tran_veg_col) + rsub_top + qflx_rsub_sat, dt, s.wa) +
-      (wl1 + pair_xor(wl1));
-  const float imb = w1 - w0;
-  if (!(fabsf(imb) <= 0.1f)) fault |= FAULT_IMBAL;
-
-  /* :1282-1283 */
-  const float r1 = qflx_surf * dt, r2 = rsub_top * dt;
-  s.rnf_sum = fmaf(rsub_top, dt, fmaf(qflx_surf, dt, s.rnf_sum));
 
   o.qflx_tran_veg_col = qflx_tran_veg_col;
   o.qflx_evap_grnd = qflx_evap_grnd;
-  o.rnf_inc = r1 + r2;
+  o.rnf_inc = rnf_inc;
   o.imbalance = imb;
   o.jwt = (jwt < 0) ? find_jwt(g, zwt_j) : jwt;
-  return fault;
+  return fault | fault_bal;
 }
 
 } /* namespace h9 */

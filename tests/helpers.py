@@ -18,8 +18,12 @@ def make_oracle(world, nisurf=48, nyr=1, kind="f32", loop_order=1, smp_leak=0, n
     return o
 
 
-THREAD_PER_CELL = 64   # h9_set_tuning block: thread-per-cell kernel, 64 threads per block
+THREAD_PER_CELL = 64   # h9_set_tuning block: thread-per-cell kernel, 64 threads per block, all
+                       # registers: the small-shard step (all-deep / general straight-line tails)
+THREAD_128REG = 1128   # thread-per-cell kernel compiled for <=128 registers: the throughput step
 TWO_LANES = 4000       # the two-lanes-per-cell kernel (small shards)
+FAST_KERNELS = [THREAD_PER_CELL, THREAD_128REG, TWO_LANES]
+FAST_KERNEL_IDS = ["thread_per_cell", "thread_per_cell_128reg", "two_lanes"]
 
 
 def make_gpu(world, nisurf=48, nyr=1, mode=0, device=0, block=0):

@@ -54,10 +54,12 @@ def test_full_size_invariants_and_determinism(big):
 
 @pytest.mark.parametrize("nranks", [2, 8])
 def test_latitude_band_shards_reproduce_the_whole(big, nranks):
-    """Bit for bit, with the stepping kernel pinned (h9_set_tuning): every launch shape of the
-    thread-per-cell kernel gives the same bits, so any split reproduces the unsplit run."""
+    """Bit for bit, with the shards' stepping kernel pinned to thread-per-cell (h9_set_tuning):
+    every launch shape and both builds of that kernel give the same bits (the whole grid steps
+    with the 128-register build, the shards with the all-register build and its straight-line
+    tails), so any split reproduces the unsplit run."""
     w, f = big
-    _, whole, ann, _ = run(w, f, block=THREAD_PER_CELL)
+    _, whole, ann, _ = run(w, f)  # automatic: the 128-register build (throughput step) at this size
     lat_s, lat_c, n_land = partition_lat_bands(w.soil_tex, w.theta_s, nranks)
     assert n_land.sum() == synth.N_LAND_HALF_DEG and lat_c.sum() == w.ny
     assert n_land.max() - n_land.min() <= 2 * w.nx   # balanced to within a couple of rows

@@ -21,8 +21,8 @@ import numpy as np
 import pytest
 
 import oracle_py
-from helpers import (THREAD_PER_CELL, TWO_LANES, assert_state_close, assert_state_equal, day_slice,
-                     make_gpu, make_oracle)
+from helpers import (FAST_KERNEL_IDS, FAST_KERNELS, THREAD_128REG, THREAD_PER_CELL, TWO_LANES,
+                     assert_state_close, assert_state_equal, day_slice, make_gpu, make_oracle)
 from hybrid9_b200 import MATH_EXACT, MATH_FAST, synth
 from hybrid9_b200.state import init_state
 
@@ -190,7 +190,7 @@ def test_exact_vs_oracle_30_days(world, forcing30, which):
 # ---- fast mode vs the oracle, against the rounding-noise floor -----------------------------
 
 
-@pytest.mark.parametrize("block", [THREAD_PER_CELL, TWO_LANES], ids=["thread_per_cell", "two_lanes"])
+@pytest.mark.parametrize("block", FAST_KERNELS, ids=FAST_KERNEL_IDS)
 @pytest.mark.parametrize("which", ["init", "random"])
 def test_fast_vs_oracle_30_days(world, forcing30, which, block):
     """H9_MATH_FAST (MUFU pow/exp/rcp, FMA contraction), both stepping kernels (thread per
@@ -216,7 +216,7 @@ def test_fast_vs_oracle_30_days(world, forcing30, which, block):
     got = h.get_state()
     rel = relerr(got.h2osoi_liq[land], res["f32"].h2osoi_liq[land])
     noise = relerr(res["f32"].h2osoi_liq[land], res["f64"].h2osoi_liq[land])
-    record(f"fast_vs_oracle_{which}_30d_{'pair' if block == TWO_LANES else 'thread'}", h2o_rel_p50=np.median(rel), h2o_rel_p999=np.quantile(rel, 0.999),
+    record(f"fast_vs_oracle_{which}_30d_{FAST_KERNEL_IDS[FAST_KERNELS.index(block)]}", h2o_rel_p50=np.median(rel), h2o_rel_p999=np.quantile(rel, 0.999),
            h2o_rel_max=rel.max(), noise_p50=np.median(noise), noise_p999=np.quantile(noise, 0.999),
            noise_max=noise.max(), zwt_abs_max=np.abs(got.zwt[land] - res["f32"].zwt[land]).max(),
            lai_rel_max=relerr(got.lai[land], res["f32"].lai[land]).max())
@@ -229,7 +229,7 @@ def test_fast_vs_oracle_30_days(world, forcing30, which, block):
     h.close()
 
 
-@pytest.mark.parametrize("block", [THREAD_PER_CELL, TWO_LANES], ids=["thread_per_cell", "two_lanes"])
+@pytest.mark.parametrize("block", FAST_KERNELS, ids=FAST_KERNEL_IDS)
 def test_fast_single_substep_vs_oracle(world, forcing30, block):
     """One sub-step from randomised (deliberately extreme) states, fast mode: 99 % of soil
     water within 1e-3 relative, every value within 2e-2 relative + 0.05 mm, and the worst
@@ -250,7 +250,7 @@ def test_fast_single_substep_vs_oracle(world, forcing30, block):
     ok = land & (np.abs(oo["w_imbalance"]) <= 0.05) & (np.abs(go["w_imbalance"]) <= 0.05)
     rel = relerr(got.h2osoi_liq[ok], ref.h2osoi_liq[ok])
     noise = relerr(ref.h2osoi_liq[ok], o64.get_state().h2osoi_liq[ok])
-    record(f"fast_single_step_{'pair' if block == TWO_LANES else 'thread'}", h2o_rel_p50=np.median(rel), h2o_rel_p99=np.quantile(rel, 0.99),
+    record(f"fast_single_step_{FAST_KERNEL_IDS[FAST_KERNELS.index(block)]}", h2o_rel_p50=np.median(rel), h2o_rel_p99=np.quantile(rel, 0.99),
            h2o_rel_max=rel.max(), noise_p99=np.quantile(noise, 0.99), noise_max=noise.max(),
            n_cells=int(ok.sum()), jwt_agree=(go["jwt"][ok] == oo["jwt"][ok]).mean())
     assert np.median(rel) < 1e-5
@@ -273,7 +273,10 @@ def test_run_days_equals_device_resident_path(world, forcing30, mode):
     f = {k: np.ascontiguousarray(v[:nd]) for k, v in forcing30.items()}
     yi = np.concatenate([np.full(6, 1, np.int32), np.full(nd - 6, 2, np.int32)])
     results = []
-    for tile, block, device_path in ((8, 64, False), (3, 32, False), (5, 128, False), (8, 64, True)):
+    # every launch shape and both builds of the thread-per-cell kernel (all registers: the
+    # small-shard step with its straight-line tails; 128 registers: the throughput step)
+    for tile, block, device_path in ((8, 64, False), (3, 32, False), (5, 128, False), (8, 64, True),
+                                     (8, THREAD_128REG, False), (4, 1032, True)):
         h = make_gpu(world, mode=mode, nyr=2)
         h.set_tuning(tile, block)
         h.set_state(st)

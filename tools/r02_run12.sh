@@ -1,0 +1,9 @@
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_pair.py tests/test_ref_golden.py tests/test_gpu_api.py tests/test_gpu_comm.py -q 2>&1 | tail -30
+rm -f gpurun_out/r02_v6.txt
+for band in 4 0 2 6; do for blk in 64 4000; do
+  H9_BENCH_BAND=$band H9_BLOCK=$blk python bench.py --grid band8 --steps 5 --warmup 3 --no-cpu --no-e2e 2>gpurun_out/r02_b.err | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('band $band block $blk', d['config']['kernel_variant'], 'ms', round(d['ms_per_step'], 3), 'shallow', d['config']['share_cells_water_table_in_soil_column_at_end'])" >> gpurun_out/r02_v6.txt
+done; done
+cat gpurun_out/r02_v6.txt
+python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_fullsize_oracle.py -q 2>&1 | tail -30
