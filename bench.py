@@ -82,8 +82,11 @@ def grid_spec(name):
         return dict(nx=720, ny=360, n_land=67420, label="regional 100x74 window of the 0.5deg mask "
                     "(2,500 land cells)", window=synth_regional_window())
     if name == "band8":
-        return dict(nx=720, ny=360, n_land=67420, band=(int(os.environ.get("H9_BENCH_BAND", "0")), 8),
-                    label="first of 8 latitude bands of the 0.5deg mask (one GPU's share of an 8-GPU strong-scaling run)")
+        nb = int(os.environ.get("H9_BENCH_NBANDS", "8"))
+        k = int(os.environ.get("H9_BENCH_BAND", "0"))
+        return dict(nx=720, ny=360, n_land=67420, band=(k, nb),
+                    label=f"band {k} of {nb} latitude bands of the 0.5deg mask (one GPU's share of a "
+                          f"{nb}-GPU strong-scaling run)")
     return dict(nx=72, ny=36, n_land=674, label="tiny 5deg test grid")
 
 

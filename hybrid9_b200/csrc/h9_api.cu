@@ -107,14 +107,20 @@ int fail(h9_ctx* c, int code, const std::string& msg) {
     ctx->launches += 1;                                                                   \
   } while (0)
 
+/* `written_first`: the array is completely written (upload or kernel) before anything reads
+ * it.  With env H9_POISON=1 such arrays start as 0xFF bytes (NaN floats) instead of zeros: a
+ * run that still gives the bits of the normal run reads no uninitialised device memory
+ * (tests/test_gpu_poison.py; the stand-in for compute-sanitizer's initcheck on this pool). */
 template <class T>
-int dev_alloc(h9_ctx* ctx, T** p, size_t n, bool track = true) {
+int dev_alloc(h9_ctx* ctx, T** p, size_t n, bool track = true, bool written_first = false) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
   if (e != cudaSuccess) return fail(ctx, H9_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   /* on the ctx's own stream: it is non-blocking, so a memset on the legacy stream would not be
    * ordered before the uploads and kernels that follow */
-  e = cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+  const char* poison = getenv("H9_POISON");
+  const int fill = (written_first && poison && atoi(poison) != 0) ? 0xFF : 0;
+  e = cudaMemsetAsync(q, fill, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
   if (e != cudaSuccess) return fail(ctx, H9_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
   *p = (T*)q;
   if (track) ctx->allocs.push_back(q);
@@ -199,10 +205,11 @@ void fold_timing(h9_ctx* ctx) {
   ctx->timing.clear();
 }
 
-ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stride) {
+ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stride, size_t limit) {
   ForcingView fv;
   for (int p = 0; p < kForcingPlanes; ++p) fv.plane[p] = base + p * plane_stride;
   fv.day_stride = day_stride;
+  fv.limit = limit;
   return fv;
 }
 
@@ -506,23 +513,23 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   const size_t n = (size_t)d.ncs;
   int rc = 0;
   float *ths = nullptr, *hks = nullptr, *bs = nullptr, *ps = nullptr, *fm = nullptr;
-  rc |= dev_alloc(ctx, &d.h2o, n * NL);
-  rc |= dev_alloc(ctx, &d.smp, n * NL);
-  rc |= dev_alloc(ctx, &d.rootr, n * NL);
-  rc |= dev_alloc(ctx, &ths, n * NL);
-  rc |= dev_alloc(ctx, &hks, n * NL);
-  rc |= dev_alloc(ctx, &bs, n * NL);
-  rc |= dev_alloc(ctx, &ps, n * NL);
-  rc |= dev_alloc(ctx, &fm, n);
-  rc |= dev_alloc(ctx, &d.zwt, n);
-  rc |= dev_alloc(ctx, &d.wa, n);
-  rc |= dev_alloc(ctx, &d.lai, n);
-  rc |= dev_alloc(ctx, &d.lai_litter, n);
-  rc |= dev_alloc(ctx, &d.plant_mass, n);
-  rc |= dev_alloc(ctx, &d.plant_foliage_mass, n);
-  rc |= dev_alloc(ctx, &d.plant_length, n);
-  rc |= dev_alloc(ctx, &d.rdepth, n);
-  rc |= dev_alloc(ctx, &d.nplants, n);
+  rc |= dev_alloc(ctx, &d.h2o, n * NL, true, true);
+  rc |= dev_alloc(ctx, &d.smp, n * NL, true, true);
+  rc |= dev_alloc(ctx, &d.rootr, n * NL, true, true);
+  rc |= dev_alloc(ctx, &ths, n * NL, true, true);
+  rc |= dev_alloc(ctx, &hks, n * NL, true, true);
+  rc |= dev_alloc(ctx, &bs, n * NL, true, true);
+  rc |= dev_alloc(ctx, &ps, n * NL, true, true);
+  rc |= dev_alloc(ctx, &fm, n, true, true);
+  rc |= dev_alloc(ctx, &d.zwt, n, true, true);
+  rc |= dev_alloc(ctx, &d.wa, n, true, true);
+  rc |= dev_alloc(ctx, &d.lai, n, true, true);
+  rc |= dev_alloc(ctx, &d.lai_litter, n, true, true);
+  rc |= dev_alloc(ctx, &d.plant_mass, n, true, true);
+  rc |= dev_alloc(ctx, &d.plant_foliage_mass, n, true, true);
+  rc |= dev_alloc(ctx, &d.plant_length, n, true, true);
+  rc |= dev_alloc(ctx, &d.rdepth, n, true, true);
+  rc |= dev_alloc(ctx, &d.nplants, n, true, true);
   rc |= dev_alloc(ctx, &d.rnf_sum, n);
   rc |= dev_alloc(ctx, &d.npp_sum, n);
   rc |= dev_alloc(ctx, &d.plant_mass_sum, n);
@@ -536,9 +543,9 @@ int h9_set_soil(h9_ctx* ctx, const int32_t* soil_tex, const float* theta_s, cons
   rc |= dev_alloc(ctx, &d.first_imb, n);
   rc |= dev_alloc(ctx, &d.first_key, 1);
   rc |= dev_alloc(ctx, &d.any_fault, 1);
-  rc |= dev_alloc(ctx, &ctx->d_cell_xy, n);
-  rc |= dev_alloc(ctx, &ctx->d_step_forcing, n * kForcingPlanes);
-  rc |= dev_alloc(ctx, &ctx->d_diag, n * 13);
+  rc |= dev_alloc(ctx, &ctx->d_cell_xy, n, true, true);
+  rc |= dev_alloc(ctx, &ctx->d_step_forcing, n * kForcingPlanes, true, true);
+  rc |= dev_alloc(ctx, &ctx->d_diag, n * 13, true, true);
   rc |= dev_alloc(ctx, &ctx->d_budget, 8);
   if (rc) {
     free_land(ctx);
@@ -674,7 +681,9 @@ int h9_run_days_device(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day,
   if (ndays == 0) return H9_OK;
   if (set_device(ctx)) return H9_ERR_CUDA;
   if (upload_year_index(ctx, ndays, year_index_of_day)) return H9_ERR_CUDA;
-  if (launch_days(ctx, ndays, ctx->d_year_index, strided_view(d_forcing, day_stride, plane_stride)))
+  if (launch_days(ctx, ndays, ctx->d_year_index,
+                  strided_view(d_forcing, day_stride, plane_stride,
+                               (size_t)(ndays - 1) * day_stride + (size_t)ctx->dev.ncs)))
     return H9_ERR_CUDA;
   advance_years(ctx, ndays, year_index_of_day);
   uint32_t any = 0;
@@ -716,6 +725,7 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
       fv.plane[p] = (const float*)dp;
     }
     fv.day_stride = ctx->ngrid;
+    fv.limit = (size_t)ndays * ctx->ngrid;
     if (launch_days(ctx, ndays, ctx->d_year_index, fv, ctx->d_cell_xy)) return H9_ERR_CUDA;
     ctx->h2d += (int64_t)ndays * kForcingPlanes * ctx->dev.nc * (int64_t)sizeof(float);
     advance_years(ctx, ndays, year_index_of_day);
@@ -746,15 +756,16 @@ int h9_run_days(h9_ctx* ctx, int ndays, const int32_t* year_index_of_day, const 
       CK(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
       CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
-      if (launch_days(ctx, nd, ctx->d_year_index + d0, strided_view(ctx->d_stage[b], ctx->ngrid, plane),
-                      ctx->d_cell_xy))
+      if (launch_days(ctx, nd, ctx->d_year_index + d0,
+                      strided_view(ctx->d_stage[b], ctx->ngrid, plane, plane), ctx->d_cell_xy))
         return H9_ERR_CUDA;
     } else {
       if (stage_and_pack(ctx, b, d0, nd, src, pinned, ctx->d_packed[b])) return H9_ERR_CUDA;
       CK(cudaEventRecord(ctx->ev_packed[b], ctx->copy_stream));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_packed[b], 0));
       if (launch_days(ctx, nd, ctx->d_year_index + d0,
-                      strided_view(ctx->d_packed[b], day_stride, (size_t)ctx->dev.ncs)))
+                      strided_view(ctx->d_packed[b], day_stride, (size_t)ctx->dev.ncs,
+                                   (size_t)(nd - 1) * day_stride + (size_t)ctx->dev.ncs)))
         return H9_ERR_CUDA;
     }
     CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
@@ -958,13 +969,13 @@ int h9_hydrology_step(h9_ctx* ctx, const float* tas, const float* rlds, const fl
   diag.w_imbalance = ctx->d_diag + 11 * n;
   diag.jwt = (int32_t*)(ctx->d_diag + 12 * n);
   if (ctx->math_mode == H9_MATH_EXACT) {
-    CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
+    CKL(launch_hydrology_step_exact(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n, n),
                                     ctx->step_counter, diag));
   } else if (use_pair(ctx)) {
-    CKL(launch_hydrology_step_pair(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
+    CKL(launch_hydrology_step_pair(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n, n),
                                    ctx->step_counter, diag));
   } else {
-    CKL(launch_hydrology_step_fast_variant(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n),
+    CKL(launch_hydrology_step_fast_variant(ctx->stream, d, ctx->geo, strided_view(ctx->d_step_forcing, 0, n, n),
                                            ctx->step_counter, diag, ctx->block));
   }
   ctx->step_counter += 1;

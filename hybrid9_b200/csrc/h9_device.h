@@ -28,6 +28,7 @@ constexpr int kForcingPlanes = 7;  /* tas, rlds, rsds, huss, ps, pr, rhs (READ_P
 struct ForcingView {
   const float* plane[kForcingPlanes];
   size_t day_stride;
+  size_t limit; /* elements of one plane's view; read by -DH9_BOUNDS_CHECK builds only */
 };
 
 struct DevArrays {

@@ -36,6 +36,7 @@ __device__ __forceinline__ void store8(float* base, int c, const float (&v)[NL])
 }
 
 __device__ __forceinline__ void load_params(const DevArrays& a, int c, Params& p) {
+  H9_ASSERT(c >= 0 && c < a.ncs);
   load8(a.theta_s, c, p.theta_s);
   load8(a.hksat, c, p.hksat);
   load8(a.bsw, c, p.bsw);
@@ -60,6 +61,7 @@ __device__ __forceinline__ void load_state(const DevArrays& a, int c, State& s) 
 }
 
 __device__ __forceinline__ void store_hydro_state(const DevArrays& a, int c, const State& s) {
+  H9_ASSERT(c >= 0 && c < a.nc);
   store8(a.h2o, c, s.h2o);
   store8(a.smp, c, s.smp);
   a.zwt[c] = s.zwt;
@@ -78,6 +80,7 @@ __device__ __forceinline__ void store_grow_state(const DevArrays& a, int c, cons
 }
 
 __device__ __forceinline__ Forcing load_forcing(const ForcingView& fv, size_t off) {
+  H9_ASSERT(off < fv.limit);
   Forcing r;
   r.tas = __ldg(fv.plane[0] + off);
   r.rlds = __ldg(fv.plane[1] + off);

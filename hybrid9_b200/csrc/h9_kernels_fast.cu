@@ -20,7 +20,8 @@ namespace h9 {
 __device__ unsigned long long g_cycle_budget[kTickSegs + 2];
 /* per warp of the launch: total cycles of lane 0, and how often its sub-steps took the
  * cascade / dryness-repair branch */
-__device__ unsigned g_warp_cycles[4096], g_warp_repairs[4096], g_warp_smid[4096];
+__device__ unsigned g_warp_cycles[4096], g_warp_repairs[4096], g_warp_smid[4096], g_warp_general[4096],
+    g_warp_slow[4096];
 #endif
 
 template <int BLOCK, int MINB>
@@ -30,6 +31,9 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
                  int nt, unsigned long long step0, int cells_per_block,
                  const int32_t* __restrict__ cell_index) {
   extern __shared__ float4 smem[];
+  __shared__ float s_geo[kGeoDynFloats];
+  GeoDyn::fill(s_geo, g); /* before any thread leaves: it ends with the kernel's only barrier */
+  const GeoDyn gd{s_geo};
   /* cells_per_block <= BLOCK: the balanced launch gives every SM the same number of cells.
    * Negative: -lanes, partial warps for small shards -- only the first `lanes` lanes of each
    * warp hold a cell, so that a shard of a few thousand cells still puts one warp on every
@@ -114,10 +118,10 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       uint32_t ft;
       if (MINB == 1) {
         const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
-        ft = all_deep ? hydrology_step_fast<kStepAllDeep>(g, tbl, day, s, so H9_TICKS_ARG)
-                      : hydrology_step_fast<kStepGeneral>(g, tbl, day, s, so H9_TICKS_ARG);
+        ft = all_deep ? hydrology_step_fast<kStepAllDeep>(g, gd, tbl, day, s, so H9_TICKS_ARG)
+                      : hydrology_step_fast<kStepGeneral>(g, gd, tbl, day, s, so H9_TICKS_ARG);
       } else {
-        ft = hydrology_step_fast<kStepThroughput>(g, tbl, day, s, so H9_TICKS_ARG);
+        ft = hydrology_step_fast<kStepThroughput>(g, gd, tbl, day, s, so H9_TICKS_ARG);
       }
       if (kDeferFault) {
         const bool first = (ft != 0u) && (ft_day == 0u);
@@ -205,7 +209,16 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   if (a.real_evap) a.evap_sum[c] = evap_sum;
 #ifdef H9_CYCLE_BUDGET
   unsigned warp_repairs = tk.acc[kTickSegs - 1]; /* most often any lane took the branch */
-  for (int o = 16; o > 0; o >>= 1) warp_repairs = max(warp_repairs, __shfl_xor_sync(__activemask(), warp_repairs, o));
+  unsigned warp_general = tk.acc[kTickSegs - 2];
+  /* per lane: sub-steps that left the straight-line tail because a Drainage loop went on
+   * (recharge: s1, baseflow: s2) or the bottom layer had to search upward (s3) */
+  unsigned s1 = tk.acc[kTickSegs - 3], s2 = tk.acc[kTickSegs - 4], s3 = tk.acc[kTickSegs - 5];
+  for (int o = 16; o > 0; o >>= 1) {
+    warp_repairs = max(warp_repairs, __shfl_xor_sync(__activemask(), warp_repairs, o));
+    s1 = max(s1, __shfl_xor_sync(__activemask(), s1, o));
+    s2 = max(s2, __shfl_xor_sync(__activemask(), s2, o));
+    s3 = max(s3, __shfl_xor_sync(__activemask(), s3, o));
+  }
   if ((threadIdx.x & 31) == 0) {
     unsigned t_w;
     asm volatile("mov.u32 %0, %%clock;" : "=r"(t_w)::"memory");
@@ -213,6 +226,10 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     if (wg < 4096) {
       g_warp_cycles[wg] = t_w - t_all0;
       g_warp_repairs[wg] = warp_repairs;
+      g_warp_general[wg] = warp_general;
+      g_warp_slow[wg] = s1;
+      g_warp_slow[1024 + wg % 1024] = s2;
+      g_warp_slow[2048 + wg % 1024] = s3;
       unsigned smid, warpid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
@@ -233,6 +250,9 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
 __global__ void __launch_bounds__(128)
 hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, const ForcingView fv,
                            unsigned long long step0, const StepDiagArrays diag, int variant) {
+  __shared__ float s_geo[kGeoDynFloats];
+  GeoDyn::fill(s_geo, g);
+  const GeoDyn gd{s_geo};
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   float4 col[kFastFloatsPerCell / 4];
@@ -264,11 +284,11 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, con
   const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
   uint32_t ft;
   if (variant == kStepThroughput) {
-    ft = hydrology_step_fast<kStepThroughput>(g, tbl, day, s, so H9_TICKS_ARG);
+    ft = hydrology_step_fast<kStepThroughput>(g, gd, tbl, day, s, so H9_TICKS_ARG);
   } else if (all_deep) {
-    ft = hydrology_step_fast<kStepAllDeep>(g, tbl, day, s, so H9_TICKS_ARG);
+    ft = hydrology_step_fast<kStepAllDeep>(g, gd, tbl, day, s, so H9_TICKS_ARG);
   } else {
-    ft = hydrology_step_fast<kStepGeneral>(g, tbl, day, s, so H9_TICKS_ARG);
+    ft = hydrology_step_fast<kStepGeneral>(g, gd, tbl, day, s, so H9_TICKS_ARG);
   }
   if (ft) record_fault(a, c, sticky, ft, step0, so.imbalance);
 #pragma unroll
@@ -371,6 +391,11 @@ extern "C" int h9_debug_warp_cycles(unsigned* cycles, unsigned* repairs) {
   cudaError_t e = cudaMemcpyFromSymbol(cycles, g_warp_cycles, sizeof(unsigned) * 4096);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaMemcpyFromSymbol(repairs, g_warp_repairs, sizeof(unsigned) * 4096);
+}
+extern "C" int h9_debug_warp_general(unsigned* general, unsigned* slow) {
+  cudaError_t e = cudaMemcpyFromSymbol(general, g_warp_general, sizeof(unsigned) * 4096);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(slow, g_warp_slow, sizeof(unsigned) * 4096);
 }
 extern "C" int h9_debug_warp_smid(unsigned* smid) {
   return (int)cudaMemcpyFromSymbol(smid, g_warp_smid, sizeof(unsigned) * 4096);

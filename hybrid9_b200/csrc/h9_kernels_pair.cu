@@ -41,6 +41,9 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
                  const int32_t* __restrict__ year_index, const ForcingView fv, int cur_year,
                  int nt, unsigned long long step0, const int32_t* __restrict__ cell_index) {
   extern __shared__ float4 smem[];
+  __shared__ float s_geo[kGeoDynFloats];
+  GeoDyn::fill(s_geo, g);
+  const GeoDyn gd{s_geo};
   const int lane = threadIdx.x & 31;
   const int h = threadIdx.x & 1;
   const int cell = (blockIdx.x * BLOCK + threadIdx.x) >> 1;
@@ -102,8 +105,8 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       /* per warp and sub-step: the step without any water-table-in-column code when every cell
        * of the warp has a deep table (uniform branch), else the general straight-line step */
       const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
-      const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, pg, tbl, day, s, so, h, lane)
-                                   : hydrology_step_pair<kStepGeneral>(g, pg, tbl, day, s, so, h, lane);
+      const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane)
+                                   : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane);
       const bool first = (ft != 0u) && (ft_day == 0u);
       ft_first = first ? ft : ft_first;
       ft_ns = first ? ns : ft_ns;
@@ -192,6 +195,9 @@ __global__ void __launch_bounds__(128)
 hydrology_step_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, const ForcingView fv,
                            unsigned long long step0, const StepDiagArrays diag) {
   extern __shared__ float4 smem[];
+  __shared__ float s_geo[kGeoDynFloats];
+  GeoDyn::fill(s_geo, g);
+  const GeoDyn gd{s_geo};
   const int lane = threadIdx.x & 31;
   const int h = threadIdx.x & 1;
   const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -220,8 +226,8 @@ hydrology_step_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, con
   day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
   StepOut so;
   const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
-  const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, pg, tbl, day, s, so, h, lane)
-                               : hydrology_step_pair<kStepGeneral>(g, pg, tbl, day, s, so, h, lane);
+  const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane)
+                               : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane);
   if (ft && writer) record_fault(a, c, sticky, ft, step0, so.imbalance);
   float h2o_full[NL];
   pair_gather(s.h2o, h, pmask, h2o_full);

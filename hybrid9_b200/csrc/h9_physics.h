@@ -43,6 +43,16 @@
 #define H9_UNROLL
 #endif
 
+/* Device-side index assertions: compiled in only by -DH9_BOUNDS_CHECK (tools/bounds_check.sh,
+ * the stand-in for compute-sanitizer's memcheck on this GPU pool); a violation traps the kernel
+ * and surfaces as cudaErrorAssert through the C ABI. */
+#if defined(H9_BOUNDS_CHECK) && defined(__CUDACC__)
+#include <assert.h>
+#define H9_ASSERT(x) assert(x)
+#else
+#define H9_ASSERT(x) ((void)0)
+#endif
+
 namespace h9 {
 
 constexpr int NL = 8; /* nsoil_layers_max, SHARED.f90:294 */
@@ -367,6 +377,7 @@ H9_HD int find_jwt(const Geo& g, float zwt) {
 /* arr[idx] for a register array indexed 0..N-1, without dynamic indexing */
 template <int N>
 H9_HD float pick(const float (&a)[N], int idx) {
+  H9_ASSERT(idx >= 0 && idx < N);
   float r = a[0];
   H9_UNROLL
   for (int k = 1; k < N; ++k)

@@ -87,6 +87,7 @@ struct CellTable {
   __device__ __forceinline__ float4 g1(int i) const { return base[(1 * NL + i) * STRIDE]; }
   __device__ __forceinline__ float4 g2(int i) const { return base[(2 * NL + i) * STRIDE]; }
   __device__ __forceinline__ float comp(int gi, int i, int k) const {
+    H9_ASSERT(gi >= 0 && gi <= kFastGroups && i >= 0 && i < NL && k >= 0 && k < 4);
     return reinterpret_cast<const float*>(&base[(gi * NL + i) * STRIDE])[k];
   }
   __device__ __forceinline__ float psi(int i) const { return comp(0, i, 0); }
@@ -200,9 +201,32 @@ __device__ __forceinline__ float fast_specific_yield(const C& c, int i, float zw
  * Same operations on the same operands as before the re-ordering. */
 enum : int { kStepThroughput = 0, kStepAllDeep = 1, kStepGeneral = 2 };
 
+/* zi, zi/1000 and zc for layer indices that are only known at run time (the Drainage code).
+ * One copy per block in shared memory: 30 floats in 30 different banks, so lanes that ask for
+ * different layers are served in one pass.  The same lookups through the constant bank replay
+ * once per distinct index -- measured on the general straight-line tail, where all 32 lanes
+ * ask: 2,900 cycles per sub-step against 1,640 for the all-deep step. */
+constexpr int kGeoDynFloats = 32;
+struct GeoDyn {
+  const float* p;
+  __device__ __forceinline__ float zi(int i) const { H9_ASSERT(i >= 0 && i <= 9); return p[i]; }
+  __device__ __forceinline__ float zim(int i) const { H9_ASSERT(i >= 0 && i <= 9); return p[10 + i]; }
+  __device__ __forceinline__ float zc(int i) const { H9_ASSERT(i >= 0 && i <= 9); return p[20 + i]; }
+  /* every thread of the block calls it before the first use (it ends with a barrier) */
+  static __device__ __forceinline__ void fill(float* sh, const Geo& g) {
+    if (threadIdx.x < 10) {
+      sh[threadIdx.x] = g.zi[threadIdx.x];
+      sh[10 + threadIdx.x] = g.zim[threadIdx.x];
+      sh[20 + threadIdx.x] = g.zc[threadIdx.x];
+    }
+    __syncthreads();
+  }
+};
+
 template <int MODE, class C>
-__device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c, const DayFast& d,
-                                                        FastState& s, StepOut& o H9_TICKS_PARAM) {
+__device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const GeoDyn& gd, const C& c,
+                                                        const DayFast& d, FastState& s,
+                                                        StepOut& o H9_TICKS_PARAM) {
   constexpr float kLog2e = 1.4426950408889634f;
   uint32_t fault = 0;
   const float dt = g.dt, rdt = g.rdt;
@@ -436,7 +460,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     for (int k = 1; k < NL; ++k)
       if (jm == k) zq_j = zq[k];
     const float wh = smp1 - zq_j;
-    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jc]) * 2.0f;
+    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - gd.zc(jc)) * 2.0f;
     qcharge_early = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
     sy_first = fast_specific_yield(c, jc, zwtmm); /* layer jwt+1 */
@@ -563,7 +587,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     }
     s.h2o[NL - 1] += xs;  /* :1205 */
     rsub_top -= xs * rdt; /* :1211 */
-    balance(qflx_rsub_sat);
+    return qflx_rsub_sat;
   };
   /* Recharge :896-904, Drainage :946-951 and baseflow :1048-1058 of a water table below the
    * column, straight-line.  jwt stays NL: it is not recomputed on this path (G10) */
@@ -587,22 +611,24 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     float qcharge_tot = qcharge * dt;
     if (qcharge_tot > 0.0f) { /* rising, layers jwt+1 .. 1 */
       for (int I = jwt + 1; I >= 1; --I) {
+        H9_ASSERT(I >= 1 && I <= NL);
         const float s_y = (I == jfirst) ? sy1 : fast_specific_yield(c, I - 1, zwtmm);
-        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
+        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - gd.zi(I - 1))), 0.0f);
         s.zwt -= ql * MathFast::rcp(s_y) * 0.001f; /* s_y >= 0.02 > 0 */
         qcharge_tot -= ql;
         if (qcharge_tot <= 0.0f) break;
       }
     } else { /* deepening, layers jwt+1 .. 8 */
       for (int I = jwt + 1; I <= NL; ++I) {
+        H9_ASSERT(I >= 1 && I <= NL);
         const float s_y = (I == jfirst) ? sy1 : fast_specific_yield(c, I - 1, zwtmm);
-        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
+        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (gd.zi(I) - zwtmm)), 0.0f);
         qcharge_tot -= ql;
         if (qcharge_tot >= 0.0f) {
           s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
           break;
         }
-        s.zwt = g.zim[I];
+        s.zwt = gd.zim(I);
       }
       if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
     }
@@ -622,8 +648,9 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
         fault_tail |= FAULT_RSUB;
       } else {
         for (int I = jwt + 1; I <= NL; ++I) {
+          H9_ASSERT(I >= 1 && I <= NL);
           const float s_y = fast_specific_yield(c, I - 1, zwtmm);
-          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
+          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (gd.zi(I) - zwtmm))), 0.0f);
 #pragma unroll
           for (int k = 0; k < NL; ++k)
             s.h2o[k] = (k == I - 1) ? s.h2o[k] + rl : s.h2o[k]; /* a select, not a jump table */
@@ -632,7 +659,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
             s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
             break;
           }
-          s.zwt = g.zim[I];
+          s.zwt = gd.zim(I);
         }
         s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* residual, unconditional :1100-1101 */
         s.wa += rsub_top_tot;
@@ -654,26 +681,29 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     for (int k = 1; k < NL; ++k)
       if (jm == k) zq_j = zq[k];
     const float wh = smp1 - zq_j;
-    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jwt]) * 2.0f;
+    H9_ASSERT(jwt >= 0 && jwt < NL);
+    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - gd.zc(jwt)) * 2.0f;
     qcharge = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
     qcharge = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge));
     sy1 = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
   };
 
   if (MODE == kStepThroughput) {
-    /* many warps per scheduler: fewest instructions; one branch on `deep`, the old trigger */
+    /* many warps per scheduler: fewest instructions executed; one branch on `deep`, then the
+     * trigger, the rarely taken repair, and the balance once */
     if (deep) {
       back_substitute();
       deep_tail();
-      finish();
     } else {
       float qcharge, sy1;
       shallow_inputs(qcharge, sy1);
       back_substitute();
       shallow_tail(qcharge, sy1);
-      finish();
     }
-    if (needfix) repair();
+    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
+    float qsat = 0.0f;
+    if (excess_tree() > 0.0f || lowest_tree() < kWatmin) qsat = repair();
+    balance(qsat);
   } else if (MODE == kStepAllDeep) {
     /* every cell of the warp has its table below the column: no branch but the rare repair */
     back_substitute();
@@ -682,7 +712,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     if (needfix) {
 #pragma unroll
       for (int i = 0; i < NL; ++i) s.h2o[i] = h_pre[i]; /* the cascade comes first */
-      repair();
+      balance(repair());
     }
   } else {
     /* General straight-line tail: the FIRST iteration of each Drainage loop (:961-1009,
@@ -698,15 +728,16 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     for (int i = 0; i < NL; ++i) h_bs[i] = s.h2o[i];
     const float qcharge = deep ? dwat2[NL] * dz9 * rdt : qcharge_early;
     const float qtot = qcharge * dt;
+    H9_ASSERT(jc >= 0 && jc + 1 <= NL);
     /* Drainage, first layer (jc = jwt, the layer holding the table) */
     const bool up = qtot > 0.0f;
-    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - g.zi[jc])), 0.0f);
-    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (g.zi[jc + 1] - zwtmm)), 0.0f);
+    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - gd.zi(jc))), 0.0f);
+    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (gd.zi(jc + 1) - zwtmm)), 0.0f);
     const float ql = up ? ql_up : ql_dn;
     const float qrem = qtot - ql;
     const float zmove = zwt0 - ql * MathFast::rcp(sy_first) * 0.001f;
     const bool done_dn = qrem >= 0.0f;
-    const float zwt1_sh = (up || done_dn) ? zmove : g.zim[jc + 1];
+    const float zwt1_sh = (up || done_dn) ? zmove : gd.zim(jc + 1);
     const bool more1 = up ? (qrem > 0.0f && jc >= 1) : (!done_dn && jc + 2 <= NL);
     const float zwt1 = deep ? fmaf(-(qcharge * dt * 0.001f), rrous_early, zwt0) : zwt1_sh;
     const float wa1 = deep ? fmaf(qcharge, dt, wa0) : wa0;
@@ -720,12 +751,13 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     for (int I = 1; I <= NL; ++I) cnt2 += (zwt1 > g.zim[I]) ? 1 : 0;
     const bool isA = deep || cnt2 == NL; /* table below the column: :1048-1058 */
     const int j2c = (cnt2 < NL) ? cnt2 : NL - 1;
+    H9_ASSERT(j2c >= 0 && j2c + 1 <= NL);
     const float sy2 = fast_specific_yield(c, j2c, zwtmm1);
     const float rtot = -rsub_top * dt;
-    const float rl = fminf(fmaxf(rtot, -(sy2 * (g.zi[j2c + 1] - zwtmm1))), 0.0f);
+    const float rl = fminf(fmaxf(rtot, -(sy2 * (gd.zi(j2c + 1) - zwtmm1))), 0.0f);
     const float rrem = rtot - rl;
     const bool done2 = rrem >= 0.0f;
-    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : g.zim[j2c + 1];
+    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : gd.zim(j2c + 1);
     const bool more2 = !isA && ((!done2 && j2c + 2 <= NL) || rtot > 0.0f);
     const float zwt_c = zwt_b - rrem * 0.001f * rrous; /* residual, unconditional :1100-1101 */
     const float wa_c = wa1 + rrem;
@@ -738,7 +770,10 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     for (int k = 0; k < NL; ++k) s.h2o[k] = (!isA && k == j2c) ? s.h2o[k] + rl : s.h2o[k];
     s.h2o[NL - 1] += isA ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
     s.wa = isA ? fminf(wa2, 5000.0f) : wa2;
-    /* clamp, triggers, the dryness pass where it cannot move the table, balance */
+    /* clamp :1122-1123, triggers, the dryness pass where it cannot move the table (jwt == NL,
+     * :1166), balance.  A straight-line cascade :1131-1152 was measured too: it lengthens the
+     * dependent chain of every warp on this tail by ~100 cycles and the cells that need it are
+     * too few to pay for that (profiles/r02/README.md), so it stays behind the rare restart. */
     s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
     const float over = excess_tree();
     const float lowest = lowest_tree();
@@ -750,6 +785,12 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
     }
     const bool fix = over > 0.0f || (isA ? (s.h2o[NL - 1] < kWatmin) : (lowest < kWatmin));
     balance(0.0f);
+#ifdef H9_CYCLE_BUDGET
+    tk.acc[kTickSegs - 2] += 1u;                                  /* general-mode sub-steps */
+    tk.acc[kTickSegs - 3] += (more1 && !deep) ? 1u : 0u;
+    tk.acc[kTickSegs - 4] += more2 ? 1u : 0u;
+    tk.acc[kTickSegs - 5] += fix ? 1u : 0u;
+#endif
     if ((more1 && !deep) || more2 || fix) { /* rare: the exact looping code from the saved state */
       s.zwt = zwt0;
       s.wa = wa0;
@@ -763,7 +804,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const C& c
         shallow_tail(qcharge_early, sy_first);
       }
       finish();
-      if (needfix) repair();
+      if (needfix) balance(repair());
     }
   }
   fault |= fault_tail;

@@ -87,6 +87,7 @@ struct PairTable {
   __device__ __forceinline__ float4 rootr4() const { return base[kPairRowRoot * STRIDE]; }
   __device__ __forceinline__ float4 misc() const { return base[kPairRowMisc * STRIDE]; }
   __device__ __forceinline__ float comp(int r, int k) const {
+    H9_ASSERT(r >= 0 && r < kPairRows && k >= 0 && k < 4);
     return reinterpret_cast<const float*>(&base[r * STRIDE])[k];
   }
   /* whole-column accessors used by the data-dependent Drainage code (dynamic layer index) */
@@ -154,6 +155,7 @@ __device__ __forceinline__ float pair_xor(float v) { return __shfl_xor_sync(kFul
 /* value of layer i (0-based, 0..7) of a per-lane array on both lanes of the pair; safe
  * inside regions where other pairs of the warp have diverged (pair mask) */
 __device__ __forceinline__ float pair_fetch(const float (&a)[NH], int i, unsigned pmask, int lane) {
+  H9_ASSERT(i >= 0 && i < NL);
   const int jl = (i < NH) ? i : NL - 1 - i;
   float v = a[0];
 #pragma unroll
@@ -182,9 +184,9 @@ __device__ __forceinline__ float pair_specific_yield(const C& c, int i, float zw
  * to the junction solve; MODE kStepAllDeep has a straight-line tail, kStepGeneral the
  * first-iteration-with-selects tail and the rare restart on the looping code. */
 template <int MODE, class C>
-__device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const PairGeo& pg, const C& c,
-                                                        const DayFast& d, PairState& s, StepOut& o,
-                                                        const int h, const int lane) {
+__device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoDyn& gd, const PairGeo& pg,
+                                                        const C& c, const DayFast& d, PairState& s,
+                                                        StepOut& o, const int h, const int lane) {
   constexpr float kLog2e = 1.4426950408889634f;
   const unsigned pmask = 3u << (lane & ~1);
   uint32_t fault = 0;
@@ -418,7 +420,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jc), 0.01f));
     const float ka = c.hks(jc) * fast_pow(s1, fmaf(2.0f, c.bsw(jc), 3.0f));
     const float wh = smp1 - zq_j;
-    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - g.zc[jc]) * 2.0f;
+    const float denom = (jc == 0) ? (zwtmm + 1.0f) : (zwtmm - gd.zc(jc)) * 2.0f;
     qcharge_early = ka * wh * MathFast::rcp(denom);
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
     sy_first = pair_specific_yield(c, jc, zwtmm);
@@ -459,24 +461,31 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
    * straight-line over the pair: layers 1..4 top-down in the even lane, the deficit of layer 4
    * handed across the junction, layers 5..7 in the odd lane (its local order is bottom-up);
    * `on` masks it per cell */
-  auto dryness_pass = [&](bool on) {
-    const bool ev = on && !odd, od = on && odd;
+  /* `jw`: jwt of the final table (NL: no layer moves it); returns the deficit of the layer
+   * right above the table, layer jw (:1166), on the lane that owns it, 0 elsewhere */
+  auto dryness_pass = [&](int jw) {
+    const bool ev = !odd && jw >= 0, od = odd && jw >= 0; /* jw < 0: the pass is off for this cell */
+    float xs_tab = 0.0f;
 #pragma unroll
-    for (int j = 0; j < NH - 1; ++j) {
+    for (int j = 0; j < NH - 1; ++j) { /* even lane: layer j+1, 1-based */
       const float xs = ev ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
+      xs_tab = (ev && j + 1 == jw) ? xs : xs_tab;
       s.h2o[j] += xs;
       s.h2o[j + 1] -= xs;
     }
-    const float xs3 = ev ? fmaxf(kWatmin - s.h2o[NH - 1], 0.0f) : 0.0f;
+    const float xs3 = ev ? fmaxf(kWatmin - s.h2o[NH - 1], 0.0f) : 0.0f; /* layer 4 */
+    xs_tab = (ev && NH == jw) ? xs3 : xs_tab;
     s.h2o[NH - 1] += xs3;
     const float pxs3 = pair_xor(xs3);
     s.h2o[NH - 1] -= od ? pxs3 : 0.0f; /* layer 5 gives to layer 4 */
 #pragma unroll
-    for (int j = NH - 1; j >= 1; --j) {
+    for (int j = NH - 1; j >= 1; --j) { /* odd lane: layer 8-j, 1-based */
       const float xs = od ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
+      xs_tab = (od && NL - j == jw) ? xs : xs_tab;
       s.h2o[j] += xs;
       s.h2o[j - 1] -= xs;
     }
+    return xs_tab;
   };
   /* excess cascade :1131-1152 and dryness repair :1161-1205 as the reference orders them, on
    * the gathered column; both lanes of the pair take the branch together */
@@ -546,7 +555,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     if (qcharge_tot > 0.0f) {
       for (int I = jwt + 1; I >= 1; --I) {
         const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
-        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - g.zi[I - 1])), 0.0f);
+        const float ql = fmaxf(fminf(qcharge_tot, s_y * (zwtmm - gd.zi(I - 1))), 0.0f);
         s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
         qcharge_tot -= ql;
         if (qcharge_tot <= 0.0f) break;
@@ -554,13 +563,13 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     } else {
       for (int I = jwt + 1; I <= NL; ++I) {
         const float s_y = (I == jfirst) ? sy_first : pair_specific_yield(c, I - 1, zwtmm);
-        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (g.zi[I] - zwtmm)), 0.0f);
+        const float ql = fminf(fmaxf(qcharge_tot, -s_y * (gd.zi(I) - zwtmm)), 0.0f);
         qcharge_tot -= ql;
         if (qcharge_tot >= 0.0f) {
           s.zwt -= ql * MathFast::rcp(s_y) * 0.001f;
           break;
         }
-        s.zwt = g.zim[I];
+        s.zwt = gd.zim(I);
       }
       if (qcharge_tot > 0.0f) s.zwt -= qcharge_tot * 0.001f * rrous_early;
     }
@@ -580,7 +589,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
       } else {
         for (int I = jwt + 1; I <= NL; ++I) {
           const float s_y = pair_specific_yield(c, I - 1, zwtmm);
-          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (g.zi[I] - zwtmm))), 0.0f);
+          const float rl = fminf(fmaxf(rsub_top_tot, -(s_y * (gd.zi(I) - zwtmm))), 0.0f);
           const int jl = (I - 1 < NH) ? I - 1 : NL - I; /* local index of layer I */
           const bool mine = ((I - 1 >= NH) == odd);
 #pragma unroll
@@ -590,7 +599,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
             s.zwt -= rl * MathFast::rcp(s_y) * 0.001f;
             break;
           }
-          s.zwt = g.zim[I];
+          s.zwt = gd.zim(I);
         }
         s.zwt -= rsub_top_tot * 0.001f * MathFast::rcp(rous); /* :1100-1101, unconditional (G11) */
         s.wa += rsub_top_tot;
@@ -614,7 +623,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     float h_pre[NH];
 #pragma unroll
     for (int j = 0; j < NH; ++j) h_pre[j] = s.h2o[j];
-    dryness_pass(true);
+    dryness_pass(NL);
     balance(0.0f, kFullMask);
     /* layer 8 (the odd lane's j = 0) is not reached by the pass: :1181-1198 is in the branch */
     if (merge_flags(over > 0.0f || (odd && s.h2o[0] < kWatmin), kFullMask)) {
@@ -630,14 +639,15 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     for (int j = 0; j < NH; ++j) h_bs[j] = s.h2o[j];
     const float qcharge = deep ? dwat9 * dz9 * rdt : qcharge_early;
     const float qtot = qcharge * dt;
+    H9_ASSERT(jc >= 0 && jc + 1 <= NL);
     const bool up = qtot > 0.0f;
-    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - g.zi[jc])), 0.0f);
-    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (g.zi[jc + 1] - zwtmm)), 0.0f);
+    const float ql_up = fmaxf(fminf(qtot, sy_first * (zwtmm - gd.zi(jc))), 0.0f);
+    const float ql_dn = fminf(fmaxf(qtot, -sy_first * (gd.zi(jc + 1) - zwtmm)), 0.0f);
     const float ql = up ? ql_up : ql_dn;
     const float qrem = qtot - ql;
     const float zmove = zwt0 - ql * MathFast::rcp(sy_first) * 0.001f;
     const bool done_dn = qrem >= 0.0f;
-    const float zwt1_sh = (up || done_dn) ? zmove : g.zim[jc + 1];
+    const float zwt1_sh = (up || done_dn) ? zmove : gd.zim(jc + 1);
     const bool more1 = up ? (qrem > 0.0f && jc >= 1) : (!done_dn && jc + 2 <= NL);
     const float zwt1 = deep ? fmaf(-(qcharge * dt * 0.001f), rrous_early, zwt0) : zwt1_sh;
     const float wa1 = deep ? fmaf(qcharge, dt, wa0) : wa0;
@@ -650,12 +660,13 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     for (int I = 1; I <= NL; ++I) cnt2 += (zwt1 > g.zim[I]) ? 1 : 0;
     const bool isA = deep || cnt2 == NL;
     const int j2c = (cnt2 < NL) ? cnt2 : NL - 1;
+    H9_ASSERT(j2c >= 0 && j2c + 1 <= NL);
     const float sy2 = pair_specific_yield(c, j2c, zwtmm1);
     const float rtot = -rsub_top * dt;
-    const float rl = fminf(fmaxf(rtot, -(sy2 * (g.zi[j2c + 1] - zwtmm1))), 0.0f);
+    const float rl = fminf(fmaxf(rtot, -(sy2 * (gd.zi(j2c + 1) - zwtmm1))), 0.0f);
     const float rrem = rtot - rl;
     const bool done2 = rrem >= 0.0f;
-    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : g.zim[j2c + 1];
+    const float zwt_b = done2 ? zwt1 - rl * MathFast::rcp(sy2) * 0.001f : gd.zim(j2c + 1);
     const bool more2 = !isA && ((!done2 && j2c + 2 <= NL) || rtot > 0.0f);
     const float zwt_c = zwt_b - rrem * 0.001f * rrous;
     const float wa_c = wa1 + rrem;
@@ -672,10 +683,12 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const Pair
     }
     s.h2o[0] += (isA && odd) ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
     s.wa = isA ? fminf(wa2, 5000.0f) : wa2;
+    /* clamp, triggers, the dryness pass where it cannot move the table, balance (see the general
+     * tail of hydrology_step_fast) */
     s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
     const float over = excess_local();
     const float lowest = lowest_local();
-    dryness_pass(isA);
+    dryness_pass(isA ? NL : -1);
     balance(0.0f, kFullMask);
     const bool fix_local = (more1 && !deep) || more2 || over > 0.0f ||
                            (isA ? (odd && s.h2o[0] < kWatmin) : (lowest < kWatmin));

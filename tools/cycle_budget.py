@@ -26,7 +26,7 @@ SEG = ["block A head: theta, w0, fsat, beta, energy balance, infiltration, aquif
        "fault bookkeeping, loop"]
 
 
-def run(lib, band, days, cell, block):
+def run(lib, band, days, cell, block, spin=3):
     env = dict(os.environ, H9GPU_LIB=lib, H9_BUDGET_CELL=str(cell))
     code = f"""
 import sys, ctypes as C, json, numpy as np
@@ -44,7 +44,7 @@ h.set_soil(w.soil_tex, w.theta_s, w.hksat, w.bsw, w.psi_s, w.fmax)
 h.set_state(init_state(w.soil_tex, w.theta_s, synth.ZI_DRIVER), with_smp=False)
 p, ds, ps = h.pack_forcing(f, nd)
 yi = np.ones(nd, np.int32)
-for _ in range(3): h.run_days_device(yi, p, ds, ps)   # reach the regime of the bench (water tables settle)
+for _ in range({spin}): h.run_days_device(yi, p, ds, ps)   # reach the regime of the bench (water tables settle)
 h.reset_counters()
 h.run_days_device(yi, p, ds, ps)
 ms = h.counters()["step_kernel_ms"]
@@ -63,6 +63,11 @@ try:
     sm = (C.c_uint * 4096)()
     h.lib.h9_debug_warp_smid(sm)
     out["warp_smid"] = list(sm)[:(h.num_land + 31) // 32]
+    nw = (h.num_land + 31) // 32
+    ge, sl = (C.c_uint * 4096)(), (C.c_uint * 4096)()
+    h.lib.h9_debug_warp_general(ge, sl)
+    out["warp_general"] = list(ge)[:nw]
+    out["warp_slow"] = [list(sl)[:nw], list(sl)[1024:1024 + nw], list(sl)[2048:2048 + nw]]
     nw = (h.num_land + 31) // 32
     out["warp_cycles"] = list(cy)[:nw]
     out["warp_repairs"] = list(rp)[:nw]
@@ -94,6 +99,7 @@ def main():
     ap.add_argument("--days", type=int, default=60)
     ap.add_argument("--block", type=int, default=64)
     ap.add_argument("--mhz", type=float, default=1965.0)
+    ap.add_argument("--spin", type=int, default=3, help="launches of --days days before the measured one")
     ap.add_argument("--coarse", action="store_true", help="leave block A unfenced inside (-DH9_CYCLE_BUDGET=2)")
     a = ap.parse_args()
     name = "cycles2" if a.coarse else "cycles"
@@ -104,8 +110,8 @@ def main():
     if a.coarse:
         SEG[2] = "block A as one piece (segments 0-2 free to overlap)"
         SEG[0] = SEG[1] = "-"
-    fenced = run(lib, a.band, a.days, a.cell, a.block)
-    plain = run(os.path.join(ROOT, "hybrid9_b200", "libh9gpu.so"), a.band, a.days, a.cell, a.block)
+    fenced = run(lib, a.band, a.days, a.cell, a.block, a.spin)
+    plain = run(os.path.join(ROOT, "hybrid9_b200", "libh9gpu.so"), a.band, a.days, a.cell, a.block, a.spin)
     nsub = a.days * 48
     print(f"band {a.band} of 8 ({fenced['nc']} cells, {100 * fenced['shallow_share']:.1f} % with the water table "
           f"inside the soil column), kernel {fenced['variant']}, warp of cell {a.cell}: "
@@ -138,10 +144,17 @@ def main():
         per_sm = np.bincount(smid, minlength=148)
         sched = smid * 4 + (wid % 4)
         per_sched = np.bincount(sched)
+        ge = np.array(fenced["warp_general"], float) / nsub
+        sl = np.array(fenced["warp_slow"], float) / nsub
         for k in order:
-            print(f"    warp {k:4d}: {wc[k]:7.0f} cycles, repair branch taken in {100 * rp[k]:5.1f} % of its sub-steps, "
-                  f"{sh[k]:2d} shallow cells, SM {smid[k]} (holds {per_sm[smid[k]]} warps of this launch), hardware warp slot "
-                  f"{wid[k]} (its scheduler holds {per_sched[sched[k]]})")
+            print(f"    warp {k:4d}: {wc[k]:7.0f} cycles, {sh[k]:2d} shallow cells at the end; general step in "
+                  f"{100 * ge[k]:5.1f} % of its sub-steps; most affected lane: recharge loop went on in "
+                  f"{100 * sl[0][k]:5.1f} %, baseflow loop in {100 * sl[1][k]:5.1f} %, bottom-layer search in "
+                  f"{100 * sl[2][k]:5.1f} %, cascade/repair branch in {100 * rp[k]:5.1f} %")
+        gen = ge > 0.5
+        if gen.any() and (~gen).any():
+            print(f"  warps mostly on the all-deep step: {int((~gen).sum())}, mean {wc[~gen].mean():.0f} cycles; mostly on the "
+                  f"general step: {int(gen.sum())}, mean {wc[gen].mean():.0f}, max {wc[gen].max():.0f}")
         ft = fenced.get("feat") or {}
         for name, mm in ft.items():
             mm = np.array(mm)
