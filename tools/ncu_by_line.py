@@ -37,13 +37,16 @@ for (loc, txt), r in zip(insts, data):
 tot = sum(by.values())
 stot = sum(sb.values())
 src = {}
-for fn in ("h9_physics.h", "h9_physics_fast.cuh", "h9_kernels.cuh", "h9_kernels_fast.cu"):
+for fn in ("h9_physics.h", "h9_physics_fast.cuh", "h9_physics_pair.cuh", "h9_kernels.cuh", "h9_kernels_fast.cu",
+           "h9_kernels_pair.cu"):
     try:
         src[fn] = open(csrc + "/" + fn).read().split("\n")
     except OSError:
         pass
 print(f"total warp-level instructions {tot:.4e}")
-for loc, n in by.most_common(int(sys.argv[6]) if len(sys.argv) > 6 else 60):
+order = sb.most_common if (len(sys.argv) > 7 and sys.argv[7] == "samples") else by.most_common
+for loc, _ in order(int(sys.argv[6]) if len(sys.argv) > 6 else 60):
+    n = by[loc]
     fn, ln = loc if loc else ("?", 0)
     text = src[fn][ln - 1].strip()[:80] if fn in src and 0 < ln <= len(src[fn]) else ""
     per = f" {n / (units / 32):6.1f}/step" if units else ""
