@@ -30,7 +30,7 @@ int launch_budget(void* stream, const DevArrays& a, int iyr, double* d_budget);
 
 struct h9_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
   std::string err;
   bool configured = false, have_soil = false;
   int lon_c = 0, lat_c = 0, nisurf = 48, nyr = 1;
@@ -74,6 +74,11 @@ struct h9_ctx {
   double* d_budget_all = nullptr; /* [nyr][8]: all-reduced budget of every year slot */
   size_t gather_elems = 0;
   int gathered_year = 0;
+  /* the NCCL part of h9_annual_collective runs on comm_stream behind ev_coll_ready (budget
+   * kernel done on the stepping stream) so that the next year's stepping kernel does not queue
+   * behind it; ev_coll_done guards the year slot that collective still reads */
+  cudaEvent_t ev_coll_ready = nullptr, ev_coll_done = nullptr;
+  bool coll_inflight = false, coll_guard = false;
   /* counters */
   int64_t launches = 0, h2d = 0, d2h = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
@@ -215,6 +220,11 @@ ForcingView strided_view(const float* base, size_t day_stride, size_t plane_stri
 
 int launch_days(h9_ctx* ctx, int ndays, const int32_t* d_yi, const ForcingView& fv,
                 const int32_t* d_cell_index = nullptr) {
+  if (ctx->coll_inflight && ctx->coll_guard) {
+    /* this batch writes the annual planes of the year an unfinished collective still reads */
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_coll_done, 0));
+    ctx->coll_inflight = false;
+  }
   cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
   const bool timed = e0 && e1;
   if (timed) CK(cudaEventRecord(e0, ctx->stream));
@@ -252,6 +262,10 @@ void advance_years(h9_ctx* ctx, int ndays, const int32_t* yi) {
 }
 
 int upload_year_index(h9_ctx* ctx, int ndays, const int32_t* yi) {
+  ctx->coll_guard = false;
+  if (ctx->coll_inflight)
+    for (int d = 0; d < ndays; ++d)
+      if (yi[d] == ctx->gathered_year) ctx->coll_guard = true;
   if ((size_t)ndays > ctx->year_index_cap) {
     if (ctx->d_year_index) cudaFree(ctx->d_year_index);
     ctx->d_year_index = nullptr;
@@ -912,6 +926,7 @@ int h9_synchronize(h9_ctx* ctx) {
   if (set_device(ctx)) return H9_ERR_CUDA;
   CK(cudaStreamSynchronize(ctx->copy_stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
   return H9_OK;
 }
 
@@ -1239,6 +1254,9 @@ int h9_comm_init(h9_ctx* ctx, int nranks, int rank, const void* id) {
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
   CKN(n->CommInitRank(&ctx->comm, nranks, u, rank));
+  if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  if (!ctx->ev_coll_ready) CK(cudaEventCreateWithFlags(&ctx->ev_coll_ready, cudaEventDisableTiming));
+  if (!ctx->ev_coll_done) CK(cudaEventCreateWithFlags(&ctx->ev_coll_done, cudaEventDisableTiming));
   ctx->nranks = nranks;
   ctx->rank = rank;
   ctx->land_of_rank.clear();
@@ -1251,8 +1269,15 @@ int h9_comm_destroy(h9_ctx* ctx) {
   if (!ctx->comm) return H9_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
   nccl_api()->CommDestroy(ctx->comm);
   ctx->comm = nullptr;
+  ctx->coll_inflight = false;
+  if (ctx->ev_coll_ready) cudaEventDestroy(ctx->ev_coll_ready);
+  if (ctx->ev_coll_done) cudaEventDestroy(ctx->ev_coll_done);
+  ctx->ev_coll_ready = ctx->ev_coll_done = nullptr;
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  ctx->comm_stream = nullptr;
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->d_budget_all) cudaFree(ctx->d_budget_all);
   ctx->d_gather = nullptr;
@@ -1282,11 +1307,19 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
   if (set_device(ctx)) return H9_ERR_CUDA;
   if (comm_prepare(ctx)) return H9_ERR_CUDA;
   NcclApi* n = nccl_api();
-  /* K5 and both collectives are enqueued on the ctx's stream right behind the stepping
-   * kernel: no host synchronisation, persistent buffers, one budget slot per year */
+  /* K5 is enqueued on the stepping stream right behind the stepping kernel and writes the
+   * year's own budget slot; the two collectives follow on the communication stream behind an
+   * event: no host synchronisation, persistent buffers, and the next year's stepping kernel does
+   * not wait for NCCL */
   double* slot = ctx->d_budget_all + (size_t)(iyr - 1) * 8;
-  CKL(launch_budget(ctx->stream, ctx->dev, iyr, ctx->d_budget));
-  CKN(n->AllReduce(ctx->d_budget, slot, 8, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  if (ctx->coll_inflight) { /* the previous collective (a year ago) before its buffers are reused */
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_coll_done, 0));
+    ctx->coll_inflight = false;
+  }
+  CKL(launch_budget(ctx->stream, ctx->dev, iyr, slot));
+  CK(cudaEventRecord(ctx->ev_coll_ready, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_coll_ready, 0));
+  CKN(n->AllReduce(slot, slot, 8, ncclDouble, ncclSum, ctx->comm, ctx->comm_stream));
   /* ragged all-gather of the 13 annual-mean planes: rank r's [13][ncs_r] block lands at its
    * offset in every rank's buffer (grouped broadcasts: shards differ in size, no padding) */
   const float* mine = ctx->dev.annual + (size_t)(iyr - 1) * kAnnualPlanes * ctx->dev.ncs;
@@ -1295,7 +1328,7 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
   for (int r = 0; r < ctx->nranks; ++r) {
     const size_t cnt = (size_t)kAnnualPlanes * (size_t)ctx->stride_of_rank[r];
     ncclResult_t rr = n->Broadcast(r == ctx->rank ? (const void*)mine : (const void*)(ctx->d_gather + off),
-                                   ctx->d_gather + off, cnt, ncclFloat, r, ctx->comm, ctx->stream);
+                                   ctx->d_gather + off, cnt, ncclFloat, r, ctx->comm, ctx->comm_stream);
     if (rr != ncclSuccess) {
       n->GroupEnd();
       return fail(ctx, H9_ERR_NCCL, std::string("ncclBroadcast: ") + n->GetErrorString(rr));
@@ -1303,6 +1336,8 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
     off += cnt;
   }
   CKN(n->GroupEnd());
+  CK(cudaEventRecord(ctx->ev_coll_done, ctx->comm_stream));
+  ctx->coll_inflight = true;
   ctx->gathered_year = iyr;
   return H9_OK;
 }
@@ -1317,8 +1352,8 @@ int h9_get_gathered_annual(h9_ctx* ctx, int r, float* planes) {
   const size_t nl = (size_t)ctx->land_of_rank[r], st = (size_t)ctx->stride_of_rank[r];
   if (nl == 0) return H9_OK;
   CK(cudaMemcpy2DAsync(planes, nl * sizeof(float), ctx->d_gather + off, st * sizeof(float),
-                       nl * sizeof(float), kAnnualPlanes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                       nl * sizeof(float), kAnnualPlanes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+  CK(cudaStreamSynchronize(ctx->comm_stream));
   ctx->d2h += (int64_t)(nl * kAnnualPlanes * sizeof(float));
   return H9_OK;
 }
@@ -1329,8 +1364,8 @@ int h9_get_budget(h9_ctx* ctx, int iyr, double* budget) {
   if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_get_budget: iyr out of range");
   if (set_device(ctx)) return H9_ERR_CUDA;
   CK(cudaMemcpyAsync(budget, ctx->d_budget_all + (size_t)(iyr - 1) * 8, 8 * sizeof(double),
-                     cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                     cudaMemcpyDeviceToHost, ctx->comm_stream));
+  CK(cudaStreamSynchronize(ctx->comm_stream));
   ctx->d2h += 64;
   return H9_OK;
 }
@@ -1338,6 +1373,8 @@ int h9_get_budget(h9_ctx* ctx, int iyr, double* budget) {
 int h9_gathered_device(h9_ctx* ctx, const float** d_planes, const double** d_budget_years) {
   if (!ctx) return H9_ERR_ARG;
   if (!ctx->comm || !ctx->d_gather) return fail(ctx, H9_ERR_STATE, "h9_gathered_device: no collective has run");
+  if (set_device(ctx)) return H9_ERR_CUDA;
+  if (ctx->coll_inflight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_coll_done, 0));
   if (d_planes) *d_planes = ctx->d_gather;
   if (d_budget_years) *d_budget_years = ctx->d_budget_all;
   return H9_OK;
