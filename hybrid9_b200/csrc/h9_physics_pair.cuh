@@ -401,11 +401,11 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
    * solve (see hydrology_step_fast): jwt as a count, the Darcy recharge :866-895, the first
    * specific yield.  The warp is converged here: full-mask shuffles. */
   int jc = NL - 1;
-  float qcharge_early = 0.0f, sy_first = 0.02f;
+  float qcharge_early = 0.0f, sy_first = 0.02f, rsy_first = 50.0f;
   if (MODE == kStepGeneral) {
-    int cnt = 0;
-#pragma unroll
-    for (int I = 1; I <= NL; ++I) cnt += (s.zwt > g.zim[I]) ? 1 : 0;
+    /* (as an add tree: the count sits on the dependent chain of the tail) */
+    const int cnt = (((s.zwt > g.zim[1]) + (s.zwt > g.zim[2])) + ((s.zwt > g.zim[3]) + (s.zwt > g.zim[4]))) +
+                    (((s.zwt > g.zim[5]) + (s.zwt > g.zim[6])) + ((s.zwt > g.zim[7]) + (s.zwt > g.zim[8])));
     jc = (cnt < NL) ? cnt : NL - 1;
     const int jm = (jc > 1 ? jc : 1) - 1;
     float smp_own[NH], zq_own[NH];
@@ -424,6 +424,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     qcharge_early = ka * wh * MathFast::rcp(denom);
     qcharge_early = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge_early));
     sy_first = pair_specific_yield(c, jc, zwtmm);
+    rsy_first = MathFast::rcp(sy_first);
   }
 
   /* ------------------------------ block B ------------------------------ */
@@ -645,7 +646,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     const float ql_dn = fminf(fmaxf(qtot, -sy_first * (gd.zi(jc + 1) - zwtmm)), 0.0f);
     const float ql = up ? ql_up : ql_dn;
     const float qrem = qtot - ql;
-    const float zmove = zwt0 - ql * MathFast::rcp(sy_first) * 0.001f;
+    const float zmove = zwt0 - ql * rsy_first * 0.001f;
     const bool done_dn = qrem >= 0.0f;
     const float zwt1_sh = (up || done_dn) ? zmove : gd.zim(jc + 1);
     const bool more1 = up ? (qrem > 0.0f && jc >= 1) : (!done_dn && jc + 2 <= NL);
@@ -655,9 +656,8 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     rsub_top = 5.5E-3f * MathFast::ex2((-kFff * kLog2e) * zwt1);
     const float rous = pair_specific_yield(c, NL - 1, zwtmm1);
     const float rrous = MathFast::rcp(rous);
-    int cnt2 = 0;
-#pragma unroll
-    for (int I = 1; I <= NL; ++I) cnt2 += (zwt1 > g.zim[I]) ? 1 : 0;
+    const int cnt2 = (((zwt1 > g.zim[1]) + (zwt1 > g.zim[2])) + ((zwt1 > g.zim[3]) + (zwt1 > g.zim[4]))) +
+                     (((zwt1 > g.zim[5]) + (zwt1 > g.zim[6])) + ((zwt1 > g.zim[7]) + (zwt1 > g.zim[8])));
     const bool isA = deep || cnt2 == NL;
     const int j2c = (cnt2 < NL) ? cnt2 : NL - 1;
     H9_ASSERT(j2c >= 0 && j2c + 1 <= NL);
