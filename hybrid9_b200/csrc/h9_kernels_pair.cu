@@ -17,6 +17,15 @@
 
 namespace h9 {
 
+#ifdef H9_CYCLE_BUDGET
+/* per warp of the launch (tools/cycle_budget.py --pair): cycles in block A / tail of the
+ * all-deep and of the general step, sub-steps on each, total */
+__device__ unsigned g_pair_warp[8][4096];
+extern "C" int h9_debug_pair_budget(unsigned* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_pair_warp, sizeof(unsigned) * 8 * 4096);
+}
+#endif
+
 namespace {
 
 /* the lane's half of a [ncs][8] field: layers 1..4 in order (h = 0), layers 8..5 (h = 1) */
@@ -75,6 +84,13 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
   const size_t fcell = (size_t)(cell_index ? __ldg(cell_index + c) : c);
   Forcing fnext = load_forcing(fv, fcell);
   int iy_next = __ldg(year_index);
+#ifdef H9_CYCLE_BUDGET
+  Ticks tk;
+#pragma unroll
+  for (int k = 0; k < kTickSegs; ++k) tk.acc[k] = 0u;
+  unsigned t_all0;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(t_all0)::"memory");
+#endif
 
   for (int d = 0; d < ndays; ++d) {
     const Forcing f = fnext;
@@ -105,8 +121,8 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       /* per warp and sub-step: the step without any water-table-in-column code when every cell
        * of the warp has a deep table (uniform branch), else the general straight-line step */
       const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
-      const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane)
-                                   : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane);
+      const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane H9_TICKS_ARG)
+                                   : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane H9_TICKS_ARG);
       const bool first = (ft != 0u) && (ft_day == 0u);
       ft_first = first ? ft : ft_first;
       ft_ns = first ? ns : ft_ns;
@@ -177,6 +193,22 @@ days_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, int ndays,
     }
   }
 
+#ifdef H9_CYCLE_BUDGET
+  if (lane == 0) {
+    unsigned t_w;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t_w)::"memory");
+    const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    if (wg < 4096) {
+      g_pair_warp[0][wg] = tk.acc[0]; /* block A, all-deep */
+      g_pair_warp[1][wg] = tk.acc[1]; /* tail, all-deep */
+      g_pair_warp[2][wg] = tk.acc[5]; /* block A, general */
+      g_pair_warp[3][wg] = tk.acc[2]; /* tail, general */
+      g_pair_warp[4][wg] = tk.acc[3]; /* sub-steps all-deep */
+      g_pair_warp[5][wg] = tk.acc[4]; /* sub-steps general */
+      g_pair_warp[6][wg] = t_w - t_all0;
+    }
+  }
+#endif
   if (valid) { /* each lane stores its half of the column, the even lane the scalars */
     store_half(a.h2o, c, h, s.h2o);
     store_half(a.smp, c, h, s.smp);
@@ -226,8 +258,11 @@ hydrology_step_kernel_pair(const DevArrays a, const __grid_constant__ Geo g, con
   day_setup_fast(g, f, gs.lai, gs.lai_litter, day, tas);
   StepOut so;
   const bool all_deep = __all_sync(kFullMask, !(s.zwt <= g.zim[NL]));
-  const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane)
-                               : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane);
+#ifdef H9_CYCLE_BUDGET
+  Ticks tk;
+#endif
+  const uint32_t ft = all_deep ? hydrology_step_pair<kStepAllDeep>(g, gd, pg, tbl, day, s, so, h, lane H9_TICKS_ARG)
+                               : hydrology_step_pair<kStepGeneral>(g, gd, pg, tbl, day, s, so, h, lane H9_TICKS_ARG);
   if (ft && writer) record_fault(a, c, sticky, ft, step0, so.imbalance);
   float h2o_full[NL];
   pair_gather(s.h2o, h, pmask, h2o_full);

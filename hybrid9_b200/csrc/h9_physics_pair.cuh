@@ -186,12 +186,13 @@ __device__ __forceinline__ float pair_specific_yield(const C& c, int i, float zw
 template <int MODE, class C>
 __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoDyn& gd, const PairGeo& pg,
                                                         const C& c, const DayFast& d, PairState& s,
-                                                        StepOut& o, const int h, const int lane) {
+                                                        StepOut& o, const int h, const int lane H9_TICKS_PARAM) {
   constexpr float kLog2e = 1.4426950408889634f;
   const unsigned pmask = 3u << (lane & ~1);
   uint32_t fault = 0;
   const float dt = g.dt, rdt = g.rdt;
   const bool odd = (h != 0);
+  H9_TICK_START();
 
   /* ------------------------------ block A ------------------------------ */
   /* :141-151 */
@@ -427,6 +428,7 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     rsy_first = MathFast::rcp(sy_first);
   }
 
+  H9_TICK(MODE == kStepGeneral ? 5 : 0); /* block A: 0 = all-deep step, 5 = general step */
   /* ------------------------------ block B ------------------------------ */
   /* state update :845-850 */
 #pragma unroll
@@ -712,6 +714,10 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     }
   }
 
+  H9_TICK(MODE == kStepGeneral ? 2 : 1); /* tail: 1 = all-deep step, 2 = general step */
+#ifdef H9_CYCLE_BUDGET
+  tk.acc[MODE == kStepGeneral ? 4 : 3] += 1u; /* sub-steps on each variant */
+#endif
   o.qflx_tran_veg_col = qflx_tran_veg_col;
   o.qflx_evap_grnd = qflx_evap_grnd;
   o.rnf_inc = rnf_inc;
