@@ -1317,9 +1317,15 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
     ctx->coll_inflight = false;
   }
   CKL(launch_budget(ctx->stream, ctx->dev, iyr, slot));
+  /* a shard that fills every SM in one wave (the 128-register kernel) gains nothing from the
+   * overlap and loses SMs to the NCCL kernels (measured: 58.5 -> 69 ms per year with replicated
+   * 0.5 deg grids): there the collectives stay on the stepping stream, between two years */
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  cudaStream_t cs = (ctx->dev.nc > nsm * 8 * 32) ? ctx->stream : ctx->comm_stream;
   CK(cudaEventRecord(ctx->ev_coll_ready, ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_coll_ready, 0));
-  CKN(n->AllReduce(slot, slot, 8, ncclDouble, ncclSum, ctx->comm, ctx->comm_stream));
+  CK(cudaStreamWaitEvent(cs, ctx->ev_coll_ready, 0));
+  CKN(n->AllReduce(slot, slot, 8, ncclDouble, ncclSum, ctx->comm, cs));
   /* ragged all-gather of the 13 annual-mean planes: rank r's [13][ncs_r] block lands at its
    * offset in every rank's buffer (grouped broadcasts: shards differ in size, no padding) */
   const float* mine = ctx->dev.annual + (size_t)(iyr - 1) * kAnnualPlanes * ctx->dev.ncs;
@@ -1328,7 +1334,7 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
   for (int r = 0; r < ctx->nranks; ++r) {
     const size_t cnt = (size_t)kAnnualPlanes * (size_t)ctx->stride_of_rank[r];
     ncclResult_t rr = n->Broadcast(r == ctx->rank ? (const void*)mine : (const void*)(ctx->d_gather + off),
-                                   ctx->d_gather + off, cnt, ncclFloat, r, ctx->comm, ctx->comm_stream);
+                                   ctx->d_gather + off, cnt, ncclFloat, r, ctx->comm, cs);
     if (rr != ncclSuccess) {
       n->GroupEnd();
       return fail(ctx, H9_ERR_NCCL, std::string("ncclBroadcast: ") + n->GetErrorString(rr));
@@ -1336,7 +1342,7 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
     off += cnt;
   }
   CKN(n->GroupEnd());
-  CK(cudaEventRecord(ctx->ev_coll_done, ctx->comm_stream));
+  CK(cudaEventRecord(ctx->ev_coll_done, cs));
   ctx->coll_inflight = true;
   ctx->gathered_year = iyr;
   return H9_OK;
@@ -1351,6 +1357,7 @@ int h9_get_gathered_annual(h9_ctx* ctx, int r, float* planes) {
   for (int q = 0; q < r; ++q) off += (size_t)kAnnualPlanes * (size_t)ctx->stride_of_rank[q];
   const size_t nl = (size_t)ctx->land_of_rank[r], st = (size_t)ctx->stride_of_rank[r];
   if (nl == 0) return H9_OK;
+  CK(cudaEventSynchronize(ctx->ev_coll_done)); /* whichever stream the collective ran on */
   CK(cudaMemcpy2DAsync(planes, nl * sizeof(float), ctx->d_gather + off, st * sizeof(float),
                        nl * sizeof(float), kAnnualPlanes, cudaMemcpyDeviceToHost, ctx->comm_stream));
   CK(cudaStreamSynchronize(ctx->comm_stream));
@@ -1363,6 +1370,7 @@ int h9_get_budget(h9_ctx* ctx, int iyr, double* budget) {
   if (!ctx->comm || !ctx->d_budget_all) return fail(ctx, H9_ERR_STATE, "h9_get_budget: no collective has run");
   if (iyr < 1 || iyr > ctx->nyr) return fail(ctx, H9_ERR_ARG, "h9_get_budget: iyr out of range");
   if (set_device(ctx)) return H9_ERR_CUDA;
+  CK(cudaEventSynchronize(ctx->ev_coll_done));
   CK(cudaMemcpyAsync(budget, ctx->d_budget_all + (size_t)(iyr - 1) * 8, 8 * sizeof(double),
                      cudaMemcpyDeviceToHost, ctx->comm_stream));
   CK(cudaStreamSynchronize(ctx->comm_stream));
