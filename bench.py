@@ -497,6 +497,8 @@ def measure(args, scaling, rank, local_rank, world_size, dev, e2e, steps, sample
         e0.record(stream)
         for _ in range(nsteps):
             fn()
+        if multi:
+            h.collective_fence()  # the last year's collectives (own stream) end inside the timed region
         e1.record(stream)
         h.synchronize()
         torch.cuda.synchronize()

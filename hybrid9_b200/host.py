@@ -366,6 +366,11 @@ class H9:
         self._ck(self.lib.h9_get_gathered_annual(self.h, r, _f(out)), "h9_get_gathered_annual")
         return out
 
+    def collective_fence(self):
+        """Order later work on the ctx's stream behind the last h9_annual_collective (which may
+        run on the library's communication stream); no host synchronisation."""
+        self._ck(self.lib.h9_gathered_device(self.h, None, None), "h9_gathered_device")
+
     def get_budget(self, iyr: int) -> np.ndarray:
         out = np.zeros(8, np.float64)
         self._ck(self.lib.h9_get_budget(self.h, iyr, out.ctypes.data_as(C.POINTER(C.c_double))),
