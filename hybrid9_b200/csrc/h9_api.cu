@@ -1308,21 +1308,22 @@ int h9_annual_collective(h9_ctx* ctx, int iyr) {
   if (comm_prepare(ctx)) return H9_ERR_CUDA;
   NcclApi* n = nccl_api();
   /* K5 is enqueued on the stepping stream right behind the stepping kernel and writes the
-   * year's own budget slot; the two collectives follow on the communication stream behind an
-   * event: no host synchronisation, persistent buffers, and the next year's stepping kernel does
-   * not wait for NCCL */
+   * year's own budget slot; the two collectives follow behind an event: no host
+   * synchronisation, persistent buffers */
   double* slot = ctx->d_budget_all + (size_t)(iyr - 1) * 8;
   if (ctx->coll_inflight) { /* the previous collective (a year ago) before its buffers are reused */
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_coll_done, 0));
     ctx->coll_inflight = false;
   }
   CKL(launch_budget(ctx->stream, ctx->dev, iyr, slot));
-  /* a shard that fills every SM in one wave (the 128-register kernel) gains nothing from the
-   * overlap and loses SMs to the NCCL kernels (measured: 58.5 -> 69 ms per year with replicated
-   * 0.5 deg grids): there the collectives stay on the stepping stream, between two years */
-  int nsm = 148;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  cudaStream_t cs = (ctx->dev.nc > nsm * 8 * 32) ? ctx->stream : ctx->comm_stream;
+  /* Default: the collectives stay on the stepping stream, between two years.  Running them on
+   * the communication stream (env H9_COMM_OVERLAP=1) lets the next year's stepping kernel start
+   * at once, but the NCCL kernels then share the SMs with it, and a rank that finished early
+   * spins in them until the slowest rank arrives: measured per simulated year, one 0.5 deg grid
+   * on 2 GPUs 31.2 -> 31.1 ms, on 8 GPUs (bands of unequal cost, one warp per scheduler) 20.0 ->
+   * 21.4 ms, replicated grids 58.5 -> 69 ms (profiles/r02/README.md). */
+  static const bool overlap = [] { const char* e = getenv("H9_COMM_OVERLAP"); return e && atoi(e) != 0; }();
+  cudaStream_t cs = overlap ? ctx->comm_stream : ctx->stream;
   CK(cudaEventRecord(ctx->ev_coll_ready, ctx->stream));
   CK(cudaStreamWaitEvent(cs, ctx->ev_coll_ready, 0));
   CKN(n->AllReduce(slot, slot, 8, ncclDouble, ncclSum, ctx->comm, cs));

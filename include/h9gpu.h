@@ -251,11 +251,12 @@ int h9_partition_lat_bands(int lon_c, int lat_c, const int32_t* soil_tex, const 
  * (WRITE_NET_CDF_3DR.f90:93-94,236-257).  These entries give the host the same meeting point
  * on the device: rank 0 creates an id and broadcasts its H9_COMM_ID_BYTES bytes with the
  * host's own transport (MPI_Bcast after INIT.f90:26-38), every rank calls h9_comm_init, and
- * once per simulated year h9_annual_collective enqueues -- with no host synchronisation and
- * persistent buffers -- the budget kernel on h9_stream(), right behind the stepping kernel, and,
- * on the library's communication stream behind an event, an FP64 all-reduce of the 8 budget sums
- * of h9_annual_device in the year's own slot and a ragged all-gather of every rank's 13
- * annual-mean planes; the next year's stepping kernel does not wait for NCCL.  libnccl is loaded on first use
+ * once per simulated year h9_annual_collective enqueues on h9_stream(), right behind the
+ * stepping kernel, with no host synchronisation and persistent buffers: the budget kernel, an
+ * FP64 all-reduce of the 8 budget sums of h9_annual_device in the year's own slot, and a ragged
+ * all-gather of every rank's 13 annual-mean planes.  (Env H9_COMM_OVERLAP=1 moves the two NCCL
+ * operations to a second stream behind an event; measured slower where ranks finish a year at
+ * different times, see h9_api.cu.)  libnccl is loaded on first use
  * (dlopen "libnccl.so.2", or the path in env H9_NCCL_LIB); errors return H9_ERR_NCCL. */
 #define H9_COMM_ID_BYTES 128
 int h9_comm_unique_id(void* id /* H9_COMM_ID_BYTES */);
