@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include "h9_kernels.cuh"
 #include "h9_physics_fast.cuh"
+#include "h9_physics_fast_tp.cuh"
 
 namespace h9 {
 
@@ -113,15 +114,15 @@ days_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, int ndays,
       StepOut so;
       /* the build with all registers picks, per warp and sub-step, the step without any
        * water-table-in-column code when every cell of the warp has a deep table (a uniform
-       * branch), else the general straight-line step; the 128-register build keeps the version
-       * with the fewest instructions */
+       * branch), else the general straight-line step; the 128-register build keeps the step with
+       * the fewest executed instructions (h9_physics_fast_tp.cuh) */
       uint32_t ft;
       if (MINB == 1) {
         const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
         ft = all_deep ? hydrology_step_fast<kStepAllDeep>(g, gd, tbl, day, s, so H9_TICKS_ARG)
                       : hydrology_step_fast<kStepGeneral>(g, gd, tbl, day, s, so H9_TICKS_ARG);
       } else {
-        ft = hydrology_step_fast<kStepThroughput>(g, gd, tbl, day, s, so H9_TICKS_ARG);
+        ft = hydrology_step_fast_tp(g, tbl, day, s, so);
       }
       if (kDeferFault) {
         const bool first = (ft != 0u) && (ft_day == 0u);
@@ -284,7 +285,7 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, con
   const bool all_deep = __all_sync(__activemask(), !(s.zwt <= g.zim[NL]));
   uint32_t ft;
   if (variant == kStepThroughput) {
-    ft = hydrology_step_fast<kStepThroughput>(g, gd, tbl, day, s, so H9_TICKS_ARG);
+    ft = hydrology_step_fast_tp(g, tbl, day, s, so);
   } else if (all_deep) {
     ft = hydrology_step_fast<kStepAllDeep>(g, gd, tbl, day, s, so H9_TICKS_ARG);
   } else {

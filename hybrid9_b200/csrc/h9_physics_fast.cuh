@@ -23,6 +23,12 @@
  *     the solve are issued before it.
  * Results differ from the exact mode at rounding level only; the deviation is
  * measured against the oracle and the FP32 noise floor in tests/test_gpu_parity.py.
+ *
+ * This header holds the table, the per-day constants and the sub-step as the kernels with at
+ * most two warps per scheduler run it (small shards of a multi-GPU split): control flow laid
+ * out for a lone warp, see hydrology_step_fast below.  The sub-step of the 128-register
+ * throughput build is in h9_physics_fast_tp.cuh (round 1's control flow, same arithmetic, same
+ * bits); the two-lanes-per-cell sub-step in h9_physics_pair.cuh.
  */
 #ifndef H9_PHYSICS_FAST_CUH
 #define H9_PHYSICS_FAST_CUH
@@ -199,6 +205,7 @@ __device__ __forceinline__ float fast_specific_yield(const C& c, int i, float zw
  *   then     the clamp, the repair trigger as two max/min trees, and the water balance computed
  *            as if no repair were needed (the rarely taken repair branch redoes it).
  * Same operations on the same operands as before the re-ordering. */
+/* sub-step variants: kStepThroughput is hydrology_step_fast_tp (h9_physics_fast_tp.cuh) */
 enum : int { kStepThroughput = 0, kStepAllDeep = 1, kStepGeneral = 2 };
 
 /* zi, zi/1000 and zc for layer indices that are only known at run time (the Drainage code).
@@ -669,43 +676,7 @@ __device__ __forceinline__ uint32_t hydrology_step_fast(const Geo& g, const GeoD
     }
     zwt_j = s.zwt;
   };
-  /* the Darcy recharge and the first specific yield where block A did not prepare them */
-  auto shallow_inputs = [&](float& qcharge, float& sy1) {
-    jwt = find_jwt(g, s.zwt);
-    const int jm = (jwt > 1 ? jwt : 1) - 1;
-    const float th_j = pick<NL>(theta, jwt);
-    const float s1 = fminf(1.0f, fmaxf(th_j * c.inv_ths(jwt), 0.01f));
-    const float ka = c.hks(jwt) * fast_pow(s1, fmaf(2.0f, c.bsw(jwt), 3.0f));
-    const float smp1 = fmaxf(kSmpmin, pick<NL>(s.smp, jm));
-    float zq_j = zq[0];
-#pragma unroll
-    for (int k = 1; k < NL; ++k)
-      if (jm == k) zq_j = zq[k];
-    const float wh = smp1 - zq_j;
-    H9_ASSERT(jwt >= 0 && jwt < NL);
-    const float denom = (jwt == 0) ? (zwtmm + 1.0f) : (zwtmm - gd.zc(jwt)) * 2.0f;
-    qcharge = ka * wh * MathFast::rcp(denom); /* -ka*(0 - wh)/denom */
-    qcharge = fminf(g.q10_hi, fmaxf(g.q10_lo, qcharge));
-    sy1 = fast_specific_yield(c, jwt, zwtmm); /* layer jwt+1 */
-  };
-
-  if (MODE == kStepThroughput) {
-    /* many warps per scheduler: fewest instructions executed; one branch on `deep`, then the
-     * trigger, the rarely taken repair, and the balance once */
-    if (deep) {
-      back_substitute();
-      deep_tail();
-    } else {
-      float qcharge, sy1;
-      shallow_inputs(qcharge, sy1);
-      back_substitute();
-      shallow_tail(qcharge, sy1);
-    }
-    s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
-    float qsat = 0.0f;
-    if (excess_tree() > 0.0f || lowest_tree() < kWatmin) qsat = repair();
-    balance(qsat);
-  } else if (MODE == kStepAllDeep) {
+  if (MODE == kStepAllDeep) {
     /* every cell of the warp has its table below the column: no branch but the rare repair */
     back_substitute();
     deep_tail();
