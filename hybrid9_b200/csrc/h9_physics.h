@@ -37,9 +37,14 @@
 
 #if defined(__CUDACC__)
 #define H9_HD __host__ __device__ __forceinline__
+/* the portable double-precision log2 / exp2 of the exact mode are CALLED, not inlined, on the
+ * device: inlined into the ~50 pow/exp sites of a sub-step they made a 20,000-instruction
+ * kernel that spent its time missing the instruction cache (profiles/r02/README.md section 11) */
+#define H9_HD_CALL static __host__ __device__ __noinline__
 #define H9_UNROLL _Pragma("unroll")
 #else
 #define H9_HD inline
+#define H9_HD_CALL inline
 #define H9_UNROLL
 #endif
 
@@ -171,7 +176,7 @@ H9_HD uint64_t h9_double_to_bits(double d) {
 }
 
 /* log2(x) for finite x > 0 that is a normal double (every positive float is) */
-H9_HD double h9_log2_pos(double x) {
+H9_HD_CALL double h9_log2_pos(double x) {
   const uint64_t u = h9_double_to_bits(x);
   int e = (int)((u >> 52) & 0x7FF) - 1023;
   double m = h9_bits_to_double((u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull); /* [1,2) */
@@ -199,7 +204,7 @@ H9_HD double h9_log2_pos(double x) {
 }
 
 /* 2**y for any double y (saturates far outside the float range) */
-H9_HD double h9_exp2(double y) {
+H9_HD_CALL double h9_exp2(double y) {
   if (!(y == y)) return y;
   if (y > 300.0) y = 300.0;
   if (y < -300.0) y = -300.0;
