@@ -26,7 +26,7 @@ UNITS = {
     "h9_pack.cu": [],
     "h9_api.cu": [],
 }
-HEADERS = ["h9_physics.h", "h9_physics_fast.cuh", "h9_physics_fast_tp.cuh", "h9_physics_pair.cuh", "h9_device.h", "h9_kernels.cuh"]
+HEADERS = ["h9_physics.h", "h9_exact_tables.h", "h9_physics_fast.cuh", "h9_physics_fast_tp.cuh", "h9_physics_pair.cuh", "h9_device.h", "h9_kernels.cuh"]
 
 
 def _nvcc() -> str:

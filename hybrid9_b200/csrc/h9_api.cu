@@ -916,7 +916,7 @@ void* h9_stream(h9_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 const char* h9_kernel_variant(h9_ctx* ctx) {
   if (!ctx) return "";
-  if (ctx->math_mode == H9_MATH_EXACT) return "h9::days_kernel<MathExact,64,1>";
+  if (ctx->math_mode == H9_MATH_EXACT) return days_variant_exact(ctx->dev.nc, ctx->block);
   if (use_pair(ctx)) return "h9::days_kernel_pair<128>";
   return days_variant_fast(ctx->dev.nc, ctx->block);
 }

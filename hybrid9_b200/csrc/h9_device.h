@@ -99,6 +99,7 @@ int launch_hydrology_step_fast_variant(void* stream, const DevArrays& a, const G
                                        const StepDiagArrays& diag, int block);
 /* name of the day-kernel instantiation launch_days_fast picks for (nc, block) */
 const char* days_variant_fast(int nc, int block);
+const char* days_variant_exact(int nc, int block);
 
 /* mode-independent kernels, h9_pack.cu */
 int launch_pack_forcing(void* stream, const float* const planes[kForcingPlanes] /* each [ndays][ngrid] */,

@@ -250,6 +250,18 @@ grow_day_kernel(const DevArrays a, const __grid_constant__ Geo g, const float* _
   if (diag.fT) diag.fT[c] = go.fT;
 }
 
+/* Which build of the generic (exact-mode) day kernel: the one capped at 128 registers runs a grid
+ * of more than 8 warps per SM in one wave and is 24 % faster there (616 vs 810 ms per simulated
+ * 0.5 deg year) although it spills 424 bytes per thread; a small shard keeps the uncapped one.
+ * block 1064 = automatic, other values as documented in include/h9gpu.h. */
+inline bool days_exact_capped(int nc, int block) {
+  if (block < 1000 || block >= 2000) return false;
+  if (block != 1064) return true;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  return nc > nsm * 8 * 32;
+}
 template <class M>
 int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
                   const int32_t* d_year_index, const ForcingView& fv, int cur_year, int nt,
@@ -259,9 +271,7 @@ int launch_days_t(void* stream, const DevArrays& a, const Geo& g, int ndays,
   /* block: threads per block (32/64/128) + 1000 when the kernel variant capped at 128
    * registers per thread (16 warps per SM resident: the whole 0.5 deg grid in one wave) is
    * wanted instead of the uncapped one (255 registers, 8 warps per SM) */
-  /* the generic (exact-mode) kernel needs its registers for the double-precision pow/exp/log:
-   * the 128-register cap doubles its run time, so it is only honoured on explicit request */
-  const bool capped = block >= 1000 && block < 2000 && block != 1064;
+  const bool capped = days_exact_capped(a.nc, block);
   const int bs = block >= 2000 ? 64 : block % 1000;
 #define H9_LAUNCH(BS, MINB)                                                                      \
   days_kernel<M, BS, MINB><<<(a.nc + BS - 1) / BS, BS, 0, st>>>(                                 \

@@ -35,11 +35,13 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "h9_exact_tables.h"
+
 #if defined(__CUDACC__)
 #define H9_HD __host__ __device__ __forceinline__
-/* the portable double-precision log2 / exp2 of the exact mode are CALLED, not inlined, on the
- * device: inlined into the ~50 pow/exp sites of a sub-step they made a 20,000-instruction
- * kernel that spent its time missing the instruction cache (profiles/r02/README.md section 11) */
+/* the exact mode's pow / exp / log are CALLED, not inlined, on the device: inlined into the ~50
+ * sites of a sub-step they made a 20,000-instruction kernel that spent its time missing the
+ * instruction cache (profiles/r02/README.md section 11) */
 #define H9_HD_CALL static __host__ __device__ __noinline__
 #define H9_UNROLL _Pragma("unroll")
 #else
@@ -175,78 +177,141 @@ H9_HD uint64_t h9_double_to_bits(double d) {
 #endif
 }
 
-/* log2(x) for finite x > 0 that is a normal double (every positive float is) */
-H9_HD_CALL double h9_log2_pos(double x) {
-  const uint64_t u = h9_double_to_bits(x);
-  int e = (int)((u >> 52) & 0x7FF) - 1023;
-  double m = h9_bits_to_double((u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull); /* [1,2) */
-  if (m > 1.4142135623730951) {
-    m = m * 0.5;
-    e += 1;
-  }
-  const double f = (m - 1.0) / (m + 1.0); /* |f| <= 0.1716 */
-  const double s = f * f;
-  /* atanh series: ln(m) = 2 f (1 + s/3 + s^2/5 + ... + s^11/23) */
-  double p = 1.0 / 23.0;
-  p = fma(p, s, 1.0 / 21.0);
-  p = fma(p, s, 1.0 / 19.0);
-  p = fma(p, s, 1.0 / 17.0);
-  p = fma(p, s, 1.0 / 15.0);
-  p = fma(p, s, 1.0 / 13.0);
-  p = fma(p, s, 1.0 / 11.0);
-  p = fma(p, s, 1.0 / 9.0);
-  p = fma(p, s, 1.0 / 7.0);
-  p = fma(p, s, 1.0 / 5.0);
-  p = fma(p, s, 1.0 / 3.0);
-  p = fma(p, s, 1.0);
-  const double lnm = 2.0 * f * p;
-  return fma(lnm, 1.4426950408889634, (double)e);
+H9_HD int h9_hi_word(double d) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(d);
+#else
+  return (int)(uint32_t)(h9_double_to_bits(d) >> 32);
+#endif
+}
+H9_HD int h9_lo_word(double d) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(d);
+#else
+  return (int)(uint32_t)(h9_double_to_bits(d) & 0xFFFFFFFFull);
+#endif
+}
+H9_HD double h9_from_words(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  return h9_bits_to_double(((uint64_t)(uint32_t)hi << 32) | (uint64_t)(uint32_t)lo);
+#endif
 }
 
-/* 2**y for any double y (saturates far outside the float range) */
-H9_HD_CALL double h9_exp2(double y) {
-  if (!(y == y)) return y;
-  if (y > 300.0) y = 300.0;
-  if (y < -300.0) y = -300.0;
-  const double big = 6755399441055744.0; /* 1.5 * 2^52: round-to-nearest-integer trick */
-  const double k = (y + big) - big;
-  const double r = (y - k) * 0.6931471805599453; /* |r| <= 0.3466 */
-  /* exp(r), Taylor to r^13 */
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, r, 1.0 / 479001600.0);
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
+/* Tables of the two kernels (tools/gen_exact_tables.py; hexadecimal literals: the same bits in
+ * every build).  On the device the per-lane lookups read global memory (L1-resident; a constant
+ * bank would serialise the 32 different indices of a warp) and the polynomial coefficients sit
+ * in a constant bank, where an FP64 instruction takes them as an operand: as literals each
+ * cost two uniform moves, a fifth of the exact kernel's executed instructions. */
+struct H9Log2Row {
+  double inv_c, log2_c;
+};
+#define H9_TAB_ROW(a, b) {a, b},
+#define H9_TAB_ONE(a) a,
+#define H9_COEF_LIST(X)                                                                          \
+  X(-1.0 / 8.0) X(1.0 / 7.0) X(-1.0 / 6.0) X(1.0 / 5.0) X(-1.0 / 4.0) X(1.0 / 3.0) X(-1.0 / 2.0) \
+  X(1.4426950408889634) X(6755399441055744.0) X(-1.0 / 32.0) X(0.6931471805599453)               \
+  X(1.0 / 720.0) X(1.0 / 120.0) X(1.0 / 24.0) X(1.0 / 6.0)
+enum {
+  kH9cL8, kH9cL7, kH9cL6, kH9cL5, kH9cL4, kH9cL3, kH9cL2, kH9cLog2e, kH9cBig, kH9cM32, kH9cLn2,
+  kH9cE6, kH9cE5, kH9cE4, kH9cE3
+};
+static const H9Log2Row kH9Log2_h[47] = {H9_LOG2_TABLE(H9_TAB_ROW)};
+static const double kH9Exp2_h[32] = {H9_EXP2_TABLE(H9_TAB_ONE)};
+static const double kH9Coef_h[15] = {H9_COEF_LIST(H9_TAB_ONE)};
+#if defined(__CUDACC__)
+static __device__ const H9Log2Row kH9Log2_d[47] = {H9_LOG2_TABLE(H9_TAB_ROW)};
+static __device__ const double kH9Exp2_d[32] = {H9_EXP2_TABLE(H9_TAB_ONE)};
+static __constant__ double kH9Coef_d[15] = {H9_COEF_LIST(H9_TAB_ONE)};
+#endif
+#if defined(__CUDA_ARCH__)
+#define H9_TAB(name) name##_d
+#else
+#define H9_TAB(name) name##_h
+#endif
+#define H9_K(i) H9_TAB(kH9Coef)[i]
+
+/* log2(x) for finite x > 0 that is a normal double (every positive float is).
+ * x = 2^e * m with m in [0.70710, 1.41421) (the split is made on the high word, at sqrt(2)
+ * truncated to 20 bits); m = c (1 + r) with c = (45+i)/64 the nearest centre (c = 1 among them,
+ * so that x near 1 keeps its relative accuracy), |r| <= 0.0112;
+ * log2 x = e + log2 c + log2(e) * (r - r^2/2 + ... - r^8/8); the dropped term is below 3e-19.
+ * No division, eight dependent FMAs. */
+H9_HD double h9_log2_pos_inl(double x) {
+  int hx = h9_hi_word(x) + (0x3FF00000 - 0x3FE6A09E);
+  const int e = (hx >> 20) - 0x3FF;
+  hx = (hx & 0x000FFFFF) + 0x3FE6A09E;
+  const double m = h9_from_words(hx, h9_lo_word(x));
+  /* round(64 m) in the low word of 64 m + 1.5 * 2^52 */
+  const int i = h9_lo_word(fma(m, 64.0, H9_K(kH9cBig))) - 45; /* 0..46 */
+  const H9Log2Row row = H9_TAB(kH9Log2)[i];
+  const double r = fma(m, row.inv_c, -1.0);
+  double p = H9_K(kH9cL8);
+  p = fma(p, r, H9_K(kH9cL7));
+  p = fma(p, r, H9_K(kH9cL6));
+  p = fma(p, r, H9_K(kH9cL5));
+  p = fma(p, r, H9_K(kH9cL4));
+  p = fma(p, r, H9_K(kH9cL3));
+  p = fma(p, r, H9_K(kH9cL2));
   p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const uint64_t sc = (uint64_t)((int64_t)k + 1023) << 52; /* 2^k, k in [-300,300] */
-  return p * h9_bits_to_double(sc);
+  const double lnm = p * r;
+  return fma(lnm, H9_K(kH9cLog2e), row.log2_c + (double)e);
 }
 
-struct MathExact {
-  static constexpr bool kFast = false;
-  /* a**b with Fortran REAL semantics on the domain this path uses (a >= 0) */
-  static H9_HD float pow(float a, float b) {
+/* 2**y for any double y that is not a NaN (saturates far outside the float range).
+ * y = k/32 + r with k = round(32 y), |r| <= 1/64; 2^y = 2^(k div 32) * 2^((k mod 32)/32) * e^(r ln 2),
+ * the middle factor from the table with k div 32 added to its exponent field, the last one by
+ * its Taylor series to degree 6 (the dropped term is below 4e-18). */
+H9_HD double h9_exp2_inl(double y) {
+  const int hy = h9_hi_word(y);
+  if ((hy & 0x7FFFFFFF) >= 0x4072C000) y = hy < 0 ? -300.0 : 300.0; /* |y| >= 300, infinities */
+  const double big = H9_K(kH9cBig); /* 1.5 * 2^52: round(32 y) lands in the low word */
+  const double kb = fma(y, 32.0, big);
+  const int ki = h9_lo_word(kb);
+  const double k = kb - big;
+  const double t = fma(k, H9_K(kH9cM32), y) * H9_K(kH9cLn2); /* |t| <= 0.0109 */
+  double p = H9_K(kH9cE6);
+  p = fma(p, t, H9_K(kH9cE5));
+  p = fma(p, t, H9_K(kH9cE4));
+  p = fma(p, t, H9_K(kH9cE3));
+  p = fma(p, t, 0.5);
+  p = fma(p, t, 1.0);
+  p = fma(p, t, 1.0);
+  const double tj = H9_TAB(kH9Exp2)[ki & 31];
+  /* 2^((k mod 32)/32) * 2^(k div 32): exact, the exponent stays within [-301, 301] */
+  return h9_from_words(h9_hi_word(tj) + ((ki >> 5) << 20), h9_lo_word(tj)) * p;
+}
+
+/* a**b with Fortran REAL semantics on the domain this path uses (a >= 0) */
+H9_HD_CALL float h9_pow_f32(float a, float b) {
+  if (!(a > 0.0f && a <= FLT_MAX && fabsf(b) <= FLT_MAX)) { /* one test on the common path */
     if (b == 0.0f || a == 1.0f) return 1.0f;
     if (!(a == a) || !(b == b)) return a + b; /* NaN */
     if (a < 0.0f) return NAN;                 /* negative base, real exponent */
     if (a == 0.0f) return b > 0.0f ? 0.0f : INFINITY;
     if (a > FLT_MAX) return b > 0.0f ? a : 0.0f; /* +inf */
-    return (float)h9_exp2((double)b * h9_log2_pos((double)a));
+    /* left: b infinite, 0 < a < inf, a != 1: the product below is the right infinity */
   }
-  static H9_HD float exp(float a) { return (float)h9_exp2((double)a * 1.4426950408889634); }
-  static H9_HD float log(float a) {
-    if (!(a > 0.0f)) return a == 0.0f ? -INFINITY : NAN;
-    if (a > FLT_MAX) return a;
-    return (float)(h9_log2_pos((double)a) * 0.6931471805599453);
-  }
+  return (float)h9_exp2_inl((double)b * h9_log2_pos_inl((double)a));
+}
+H9_HD_CALL float h9_exp_f32(float a) {
+  if (!(a == a)) return a;
+  return (float)h9_exp2_inl((double)a * H9_K(kH9cLog2e));
+}
+H9_HD_CALL float h9_log_f32(float a) {
+  if (!(a > 0.0f)) return a == 0.0f ? -INFINITY : NAN;
+  if (a > FLT_MAX) return a;
+  return (float)(h9_log2_pos_inl((double)a) * H9_K(kH9cLn2));
+}
+
+struct MathExact {
+  static constexpr bool kFast = false;
+  static H9_HD float pow(float a, float b) { return h9_pow_f32(a, b); }
+  static H9_HD float exp(float a) { return h9_exp_f32(a); }
+  static H9_HD float log(float a) { return h9_log_f32(a); }
+  /* IEEE division stays inline: as a call it shrinks the kernel by a third and still runs
+   * 11 % slower (profiles/r02/README.md section 11) */
   static H9_HD float div(float a, float b) { return a / b; }
 };
 

@@ -57,8 +57,8 @@ typedef struct h9_ctx h9_ctx;
 
 /* arithmetic mode of the device kernels */
 #define H9_MATH_EXACT 0 /* every + - * / is the IEEE operation the Fortran order implies (no FMA
-                         * contraction, IEEE division); pow/exp/log by portable double-precision
-                         * kernels (IEEE double ops + fma only) whose float result is correctly
+                         * contraction, IEEE division); pow/exp/log by portable table-driven
+                         * double-precision kernels (IEEE double ops + fma) whose float result is correctly
                          * rounded: the reference's arithmetic bit for bit, the verification mode */
 #define H9_MATH_FAST 1  /* default: pow(a,b) = ex2.approx(b * lg2.approx(a)), exp by ex2.approx,
                          * 1/x by rcp.approx (MUFU), explicit FMAs, reciprocals shared and hoisted;
@@ -110,7 +110,10 @@ int h9_set_option(h9_ctx* ctx, int option, int value);
  * All thread-per-cell shapes give the same bits; the two-lanes-per-cell kernel orders the
  * tridiagonal solve and the column sums differently and agrees with them at rounding level
  * (FP32 noise floor of the model, tests/test_gpu_pair.py).  A run that must be bit-identical
- * whatever the shard size (shards == whole grid) pins the shape, e.g. block = 64.  <=0 keeps. */
+ * whatever the shard size (shards == whole grid) pins the shape, e.g. block = 64.  <=0 keeps.
+ * The exact-mode kernel is always thread per cell: threads per block as above, the 128-register
+ * build with +1000 or, under 1064, for more than 8 warps per SM of cells; every shape gives the
+ * same bits. */
 int h9_set_tuning(h9_ctx* ctx, int tile_days, int block);
 /* name of the stepping-kernel instantiation the next h9_run_days will launch */
 const char* h9_kernel_variant(h9_ctx* ctx);

@@ -112,6 +112,38 @@ def test_portable_kernels_are_correctly_rounded():
     assert lib.h9t_pow(0.01, 2e8) == 0.0 and np.isinf(lib.h9t_pow(0.01, -2e8))  # bsw = 1e8 (G28)
 
 
+def test_portable_kernels_corner_regions():
+    """The places where the table-driven kernels change regime: bases next to 1 (centre c = 1
+    of the log table), mantissas either side of the sqrt(2) split in every binade, sub-normal and
+    largest floats, saturating exponents, and the special values of the wrappers."""
+    lib = oracle_py.load_twin()
+    rng = np.random.default_rng(7)
+    n = 4000
+
+    def check(a, b):
+        got = np.array([lib.h9t_pow(float(x), float(y)) for x, y in zip(a, b)], np.float32)
+        with np.errstate(all="ignore"):
+            ref = np.power(a.astype(np.float64), b.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(got, ref), np.nonzero(got != ref)[0][:5]
+
+    check((1 + rng.uniform(-1e-3, 1e-3, n)).astype(np.float32), rng.uniform(-3000, 3000, n).astype(np.float32))
+    split = (np.float32(1.41421) + rng.uniform(-2e-5, 2e-5, n)).astype(np.float32)
+    check(split * np.exp2(rng.integers(-20, 20, n)).astype(np.float32), rng.uniform(-3, 3, n).astype(np.float32))
+    check(np.exp(rng.uniform(-103, 88, n)).astype(np.float32), rng.uniform(-3, 3, n).astype(np.float32))
+    check(np.array([1e-45, 1.1754944e-38, 3.4028235e38, 1.0, 0.5, 2.0], np.float32),
+          np.array([0.5, 0.5, 0.5, 7.0, 200.0, -200.0], np.float32))
+    inf, nan = float("inf"), float("nan")
+    assert np.isnan(lib.h9t_exp(nan)) and np.isinf(lib.h9t_exp(inf)) and lib.h9t_exp(-inf) == 0.0
+    assert np.isinf(lib.h9t_pow(2.0, inf)) and lib.h9t_pow(0.5, inf) == 0.0 and lib.h9t_pow(2.0, -inf) == 0.0
+    assert lib.h9t_pow(1.0, inf) == 1.0 and lib.h9t_pow(inf, -1.0) == 0.0 and np.isinf(lib.h9t_pow(inf, 1.0))
+    assert np.isnan(lib.h9t_pow(nan, 1.0)) and np.isnan(lib.h9t_pow(2.0, nan)) and lib.h9t_pow(nan, 0.0) == 1.0
+    assert np.isinf(lib.h9t_log(0.0)) and np.isnan(lib.h9t_log(-1.0)) and np.isinf(lib.h9t_log(inf))
+    x = np.array([-104.0, -103.9, -87.4, 88.7, 88.8, 0.0, -0.0, 1e-30], np.float32)
+    with np.errstate(over="ignore"):
+        ref = np.exp(x.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(np.array([lib.h9t_exp(float(v)) for v in x], np.float32), ref)
+
+
 def test_exact_mode_build_vs_oracle_tolerance(world):
     """Exact-mode arithmetic differs from the oracle only in pow/exp/log results that
     differ by one float ulp on rare inputs (glibc's powf is not always correctly
