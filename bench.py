@@ -394,7 +394,15 @@ def pipe_roofline(variant, units_rank, kern_ms, clocks):
     try:
         with open(pf) as f:
             pj = json.load(f)
-        k = pj["kernels"].get(variant) or pj["kernels"][pj["default"]]
+        # every launch shape of one build executes the same instructions: <BLOCK,1> is the
+        # all-registers build, <BLOCK,4|8|16> the 128-register one
+        import re
+        fam = re.sub(r"<(MathExact,)?\d+,1>", r"<\g<1>64,1>", variant or "")
+        fam = re.sub(r"<(MathExact,)?\d+,(4|8|16)>", r"<\g<1>64,8>", fam)
+        k = pj["kernels"].get(fam)
+        if k is None and "MathExact" in fam:
+            return None  # no capture of that build: no floor rather than another kernel's
+        k = k or pj["kernels"][pj["default"]]
         mhz = (clocks or {}).get("sm_mhz") or pj.get("sm_mhz", 1965.0)
         sched = pj.get("schedulers", 148 * 4)
         wsub = units_rank / float(k["cell_steps_per_warp_substep"])  # warp-sub-steps per launch

@@ -315,6 +315,23 @@ hydrology_step_kernel_fast(const DevArrays a, const __grid_constant__ Geo g, con
   if (diag.jwt) diag.jwt[c] = so.jwt;
 }
 
+/* Launch shape of the thread-per-cell kernel.  The default (1064) adapts to the shard size: up
+ * to 8 warps per SM the uncapped build (more registers, more instruction-level parallelism per
+ * warp) is faster, above that the 128-register build keeps the whole shard resident in one wave.
+ * A shard of at most 128 cells per SM goes out as ONE block of four warps per SM: the four land
+ * on the four schedulers, whereas two 64-thread blocks on an SM can put two warps on one
+ * scheduler and leave another idle (quarter of the 0.5 deg grid: 24.9 -> 21.7 ms per year).
+ * Same PTX, same results for every shape. */
+static void fast_shape(int nc, int block, int* bs, bool* capped) {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const bool small_shard = (block == 1064) && (nc <= nsm * 8 * 32);
+  *capped = block >= 1000 && !small_shard;
+  *bs = block % 1000;
+  if (small_shard && nc <= nsm * 128) *bs = 128;
+}
+
 int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
                      const int32_t* d_year_index, const ForcingView& fv, int cur_year, int nt,
                      unsigned long long step0, int block, const int32_t* d_cell_index) {
@@ -338,15 +355,9 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
         a, g, ndays, d_year_index, fv, cur_year, nt, step0, cpb, d_cell_index);
     return (int)cudaGetLastError();
   }
-  /* the default (1064) adapts to the shard size: up to 8 warps per SM the uncapped variant
-   * (more registers, more instruction-level parallelism per warp) is faster; above that the
-   * 128-register variant keeps the whole shard resident in one wave.  Same PTX, same results. */
-  int dev = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const bool small_shard = (block == 1064) && (a.nc <= nsm * 8 * 32);
-  const bool capped = block >= 1000 && !small_shard;
-  const int bs = block % 1000;
+  int bs = 64;
+  bool capped = false;
+  fast_shape(a.nc, block, &bs, &capped);
   int lanes = 32;
   if (const char* e = getenv("H9_LANES")) lanes = atoi(e) > 0 && atoi(e) <= 32 ? atoi(e) : 32;
 #define H9_LAUNCH(BS, MINB)                                                                    \
@@ -372,13 +383,10 @@ int launch_days_fast(void* stream, const DevArrays& a, const Geo& g, int ndays,
 }
 
 const char* days_variant_fast(int nc, int block) {
-  int dev = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   if (block >= 2000) return "h9::days_kernel_fast<512,1> (balanced)";
-  const bool small_shard = (block == 1064) && (nc <= nsm * 8 * 32);
-  const bool capped = block >= 1000 && !small_shard;
-  const int bs = block % 1000;
+  int bs = 64;
+  bool capped = false;
+  fast_shape(nc, block, &bs, &capped);
   if (bs == 32) return capped ? "h9::days_kernel_fast<32,16>" : "h9::days_kernel_fast<32,1>";
   if (bs == 128) return capped ? "h9::days_kernel_fast<128,4>" : "h9::days_kernel_fast<128,1>";
   return capped ? "h9::days_kernel_fast<64,8>" : "h9::days_kernel_fast<64,1>";

@@ -106,7 +106,8 @@ int h9_set_option(h9_ctx* ctx, int option, int value);
  *                     aquifer on a lane pair, tridiagonal solved from both ends);
  *   1064 (default)    automatic: two lanes per cell up to 16 cells x 4 schedulers x SMs
  *                     (9,472 on a B200; env H9_PAIR_MAX_CELLS overrides), thread per cell with
- *                     all registers up to 8 warps per SM, the 128-register build above.
+ *                     all registers up to 8 warps per SM (one 128-thread block per SM while
+ *                     the shard has at most 128 cells per SM), the 128-register build above.
  * All thread-per-cell shapes give the same bits; the two-lanes-per-cell kernel orders the
  * tridiagonal solve and the column sums differently and agrees with them at rounding level
  * (FP32 noise floor of the model, tests/test_gpu_pair.py).  A run that must be bit-identical

@@ -74,6 +74,27 @@ def test_latitude_band_shards_reproduce_the_whole(big, nranks):
         assert np.array_equal(a["rnf"], ann["rnf"][ys], equal_nan=True)
 
 
+def test_four_way_shards_with_the_automatic_shape_reproduce_the_whole(big):
+    """What a 4-GPU run does by default: a 16.9k-cell band goes out as one 128-thread block per
+    SM of the all-register thread-per-cell build.  Still thread per cell, so bit for bit the
+    unsplit run."""
+    w, f = big
+    _, whole, ann, _ = run(w, f)
+    lat_s, lat_c, n_land = partition_lat_bands(w.soil_tex, w.theta_s, 4)
+    for r in range(4):
+        ys = slice(int(lat_s[r]) - 1, int(lat_s[r]) - 1 + int(lat_c[r]))
+        sub = w.window(1, int(lat_s[r]), w.nx, int(lat_c[r]))
+        fs = {k: np.ascontiguousarray(v[:, ys, :]) for k, v in f.items()}
+        h = make_gpu(sub, mode=MATH_FAST)
+        assert h.kernel_variant() == "h9::days_kernel_fast<128,1>", h.kernel_variant()
+        h.set_state(init_state(sub.soil_tex, sub.theta_s, synth.ZI_DRIVER))
+        assert h.run_days(np.ones(ND, np.int32), fs) == 0
+        st = h.get_state()
+        h.close()
+        for n in ("h2osoi_liq", "zwt", "wa", "lai", "plant_mass", "smp"):
+            assert np.array_equal(getattr(st, n)[sub.land], getattr(whole, n)[ys][sub.land]), (r, n)
+
+
 def test_eight_way_shards_with_the_automatic_kernel_agree_with_the_whole(big):
     """What an 8-GPU run does by default: each 8.4k-cell band steps with two lanes per cell
     (two-sided tridiagonal solve), the unsplit grid with one thread per cell.  Same
