@@ -463,32 +463,42 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
   /* the dryness repair :1161-1174 for a table below the column (it cannot move zwt, :1166),
    * straight-line over the pair: layers 1..4 top-down in the even lane, the deficit of layer 4
    * handed across the junction, layers 5..7 in the odd lane (its local order is bottom-up);
-   * `on` masks it per cell */
-  /* `jw`: jwt of the final table (NL: no layer moves it); returns the deficit of the layer
-   * right above the table, layer jw (:1166), on the lane that owns it, 0 elsewhere */
-  auto dryness_pass = [&](int jw) {
-    const bool ev = !odd && jw >= 0, od = odd && jw >= 0; /* jw < 0: the pass is off for this cell */
-    float xs_tab = 0.0f;
+   * `on` masks it per cell.  With D_j = watmin - h2o_j the reference's loop is
+   * xs_j = max(0, D_j + xs_{j-1}), h2o_j = (h2o_j - xs_{j-1}) + xs_j: two dependent operations
+   * per layer in the even lane, and in the odd lane every xs as max(B, A + p) of the deficit p
+   * that arrives over the junction (A, B from the lane's own D, ready before the shuffle
+   * lands), so three operations follow the shuffle instead of nine.  A pass that finds no layer
+   * below the floor (the usual case) leaves every h2o bit for bit. */
+  /* Returns whether layer 8 ends below the floor (:1181-1198, the looping repair of the branch):
+   * the odd lane sends the three numbers that decide it while the even lane sends its deficit,
+   * and both lanes evaluate the same expression on the same operands, so the pair agrees on
+   * the branch without a second shuffle behind the pass. */
+  auto dryness_pass = [&](bool on) -> bool {
+    float D[NH];
 #pragma unroll
-    for (int j = 0; j < NH - 1; ++j) { /* even lane: layer j+1, 1-based */
-      const float xs = ev ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
-      xs_tab = (ev && j + 1 == jw) ? xs : xs_tab;
-      s.h2o[j] += xs;
-      s.h2o[j + 1] -= xs;
-    }
-    const float xs3 = ev ? fmaxf(kWatmin - s.h2o[NH - 1], 0.0f) : 0.0f; /* layer 4 */
-    xs_tab = (ev && NH == jw) ? xs3 : xs_tab;
-    s.h2o[NH - 1] += xs3;
-    const float pxs3 = pair_xor(xs3);
-    s.h2o[NH - 1] -= od ? pxs3 : 0.0f; /* layer 5 gives to layer 4 */
+    for (int j = 0; j < NH; ++j) D[j] = kWatmin - s.h2o[j];
+    /* even lane: layers 1..4 = local 0..3 */
+    const float x0 = fmaxf(D[0], 0.0f);
+    const float x1 = fmaxf(D[1] + x0, 0.0f);
+    const float x2 = fmaxf(D[2] + x1, 0.0f);
+    const float x3 = fmaxf(D[3] + x2, 0.0f);
+    const float xe = (on && !odd) ? x3 : 0.0f;
+    /* odd lane: layers 5, 6, 7 = local 3, 2, 1; layer 8 (local 0) only gives */
+    const float a6 = D[3] + D[2], b6 = fmaxf(D[2], 0.0f);
+    const float a7 = D[1] + a6, b7 = fmaxf(D[1] + b6, 0.0f);
+    const float r_b = pair_xor(b7);
+    const float r_h = pair_xor(s.h2o[0]);
+    const float r_x = pair_xor(odd ? a7 : xe); /* even lane: the odd lane's a7; odd lane: layer 4's deficit */
+    const float p = odd ? r_x : xe;
+    const float y7 = fmaxf(odd ? b7 : r_b, (odd ? a7 : r_x) + p);
+    const bool dry8 = on && ((odd ? s.h2o[0] : r_h) - y7) < kWatmin;
+    const float y5 = fmaxf(D[3] + p, 0.0f);
+    const float y6 = fmaxf(b6, a6 + p);
+    const float add[NH] = {odd ? 0.0f : x0, odd ? y7 : x1, odd ? y6 : x2, odd ? y5 : x3};
+    const float sub[NH] = {odd ? y7 : 0.0f, odd ? y6 : x0, odd ? y5 : x1, odd ? p : x2};
 #pragma unroll
-    for (int j = NH - 1; j >= 1; --j) { /* odd lane: layer 8-j, 1-based */
-      const float xs = od ? fmaxf(kWatmin - s.h2o[j], 0.0f) : 0.0f;
-      xs_tab = (od && NL - j == jw) ? xs : xs_tab;
-      s.h2o[j] += xs;
-      s.h2o[j - 1] -= xs;
-    }
-    return xs_tab;
+    for (int j = 0; j < NH; ++j) s.h2o[j] = (s.h2o[j] - (on ? sub[j] : 0.0f)) + (on ? add[j] : 0.0f);
+    return dry8;
   };
   /* excess cascade :1131-1152 and dryness repair :1161-1205 as the reference orders them, on
    * the gathered column; both lanes of the pair take the branch together */
@@ -626,10 +636,13 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     float h_pre[NH];
 #pragma unroll
     for (int j = 0; j < NH; ++j) h_pre[j] = s.h2o[j];
-    dryness_pass(NL);
+    /* the balance before the pass: the pass moves water between layers of the column, its sum
+     * is the same up to rounding (bit for bit when the pass finds nothing to do), and the pass
+     * and the balance are the two long chains at the end of the sub-step */
+    const bool fix_early = merge_flags(over > 0.0f, kFullMask);
     balance(0.0f, kFullMask);
     /* layer 8 (the odd lane's j = 0) is not reached by the pass: :1181-1198 is in the branch */
-    if (merge_flags(over > 0.0f || (odd && s.h2o[0] < kWatmin), kFullMask)) {
+    if (dryness_pass(true) || fix_early) {
 #pragma unroll
       for (int j = 0; j < NH; ++j) s.h2o[j] = h_pre[j]; /* the cascade comes first */
       repair();
@@ -690,11 +703,10 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     s.zwt = fminf(80.0f, fmaxf(0.0f, zwt_j));
     const float over = excess_local();
     const float lowest = lowest_local();
-    dryness_pass(isA ? NL : -1);
-    balance(0.0f, kFullMask);
-    const bool fix_local = (more1 && !deep) || more2 || over > 0.0f ||
-                           (isA ? (odd && s.h2o[0] < kWatmin) : (lowest < kWatmin));
-    if (merge_flags(fix_local, kFullMask)) { /* rare: the looping code from the saved state */
+    const bool fix_local = (more1 && !deep) || more2 || over > 0.0f || (!isA && lowest < kWatmin);
+    const bool fix_early = merge_flags(fix_local, kFullMask);
+    balance(0.0f, kFullMask); /* before the pass: see the all-deep tail */
+    if (dryness_pass(isA) || fix_early) { /* rare: the looping code from the saved state */
       s.zwt = zwt0;
       s.wa = wa0;
 #pragma unroll

@@ -1,4 +1,7 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/final_tests.txt 2>&1; tail -3 gpurun_out/final_tests.txt
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.txt 2>&1; tail -2 gpurun_out/final_smoke.txt
-python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -c 600 gpurun_out/final_bench.json
-ncu --set full --clock-control none --import-source on -k regex:days_kernel -c 1 -o gpurun_out/exact_final python bench.py --math exact --days 20 --steps 1 --warmup 0 --no-cpu --no-e2e > gpurun_out/exact_final_ncu.log 2>&1; tail -1 gpurun_out/exact_final_ncu.log
+out=gpurun_out/pass2.txt; : > $out
+run() { H9_BENCH_NBANDS=$1 H9_BENCH_BAND=$2 python bench.py --grid band8 --block $3 --steps 4 --warmup 3 --no-cpu --no-e2e --no-weak 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('band $2 of $1 block $3', d['config'].get('kernel_variant'), 'ms', round(d['ms_per_step'], 3))" >> $out; }
+run 8 4 0; run 8 0 0; run 8 7 0; run 8 2 0; run 8 6 0
+python -m pytest tests/test_gpu_pair.py tests/test_gpu_fullsize.py -q -x -k "not multi_decade" 2>&1 | tail -3 >> $out
+cat $out
