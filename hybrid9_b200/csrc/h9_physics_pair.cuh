@@ -433,6 +433,10 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
   /* state update :845-850 */
 #pragma unroll
   for (int j = 0; j < NH; ++j) s.h2o[j] = fmaf(dw[j + 1], pg.dz[j], s.h2o[j]);
+  /* layer 8 (the odd lane's j = 0) as the even lane will need it for the trigger at the end of
+   * the tail, sent now: what the aquifer spills into it later both lanes compute themselves */
+  const float h8_sent = pair_xor(s.h2o[0]);
+  float spill8 = 0.0f;
 
   float rsub_top;
   int jwt = NL;
@@ -487,11 +491,10 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     const float a6 = D[3] + D[2], b6 = fmaxf(D[2], 0.0f);
     const float a7 = D[1] + a6, b7 = fmaxf(D[1] + b6, 0.0f);
     const float r_b = pair_xor(b7);
-    const float r_h = pair_xor(s.h2o[0]);
     const float r_x = pair_xor(odd ? a7 : xe); /* even lane: the odd lane's a7; odd lane: layer 4's deficit */
     const float p = odd ? r_x : xe;
     const float y7 = fmaxf(odd ? b7 : r_b, (odd ? a7 : r_x) + p);
-    const bool dry8 = on && ((odd ? s.h2o[0] : r_h) - y7) < kWatmin;
+    const bool dry8 = on && ((odd ? s.h2o[0] : h8_sent + spill8) - y7) < kWatmin;
     const float y5 = fmaxf(D[3] + p, 0.0f);
     const float y6 = fmaxf(b6, a6 + p);
     const float add[NH] = {odd ? 0.0f : x0, odd ? y7 : x1, odd ? y6 : x2, odd ? y5 : x3};
@@ -557,7 +560,8 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
     const float rous = pair_specific_yield(c, NL - 1, zwtmm);
     s.wa = fmaf(-rsub_top, dt, s.wa);
     s.zwt = fmaf(rsub_top * dt * 0.001f, MathFast::rcp(rous), s.zwt);
-    s.h2o[0] += odd ? fmaxf(0.0f, s.wa - 5000.0f) : 0.0f; /* layer 8 is the odd lane's j = 0 */
+    spill8 = fmaxf(0.0f, s.wa - 5000.0f);
+    s.h2o[0] += odd ? spill8 : 0.0f; /* layer 8 is the odd lane's j = 0 */
     s.wa = fminf(s.wa, 5000.0f);
     zwt_j = s.zwt;
   };
@@ -696,7 +700,8 @@ __device__ __forceinline__ uint32_t hydrology_step_pair(const Geo& g, const GeoD
 #pragma unroll
       for (int k = 0; k < NH; ++k) s.h2o[k] = (mine && k == jl) ? s.h2o[k] + rl : s.h2o[k];
     }
-    s.h2o[0] += (isA && odd) ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
+    spill8 = isA ? fmaxf(0.0f, wa2 - 5000.0f) : 0.0f;
+    s.h2o[0] += odd ? spill8 : 0.0f;
     s.wa = isA ? fminf(wa2, 5000.0f) : wa2;
     /* clamp, triggers, the dryness pass where it cannot move the table, balance (see the general
      * tail of hydrology_step_fast) */
